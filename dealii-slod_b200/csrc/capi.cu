@@ -1,0 +1,888 @@
+// C ABI (include/slod.h) and host-side orchestration of the batched patch kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/slod.h"
+#include "geom.h"
+#include "kernels.h"
+
+using namespace slod;
+
+namespace {
+
+std::string g_create_error;
+
+struct Timings {
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+}  // namespace
+
+struct slod_ctx {
+  slod_params par{};
+  Params P{};
+  int device = 0;
+  int n_sm = 148;
+  int64_t n_patches = 0;
+  int n_fields = 1;
+  bool coef_set[2] = {false, false};
+  double *d_coef = nullptr;  // [n_fields][nsub^dim]
+  size_t coef_field_elems = 0;
+  // results owned by the handle (host-buffer API)
+  double *d_phi = nullptr, *d_aphi = nullptr, *d_Kell = nullptr, *d_diag = nullptr;
+  int *d_status = nullptr;
+  bool basis_done = false, coarse_done = false;
+  // chunk workspaces
+  int chunk = 0;
+  int *d_ids = nullptr;
+  double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr;
+  int solve_grid = 0;
+  SolveLayout sl{};
+  DenseLayout dl{};
+  SelectLayout el{};
+  FinishLayout fl{};
+  size_t smem_solve = 0, smem_dense = 0, smem_select = 0, smem_finish = 0, smem_coarse = 0;
+  int grid_solve = 0, grid_dense = 0, grid_select = 0, grid_finish = 0, grid_coarse = 0;
+  int bw_max = 0, nb_max = 0;
+  cudaEvent_t ev[10]{};
+  Timings tm;
+  int64_t launches = 0;
+  mutable std::string err;
+  // host caches
+  mutable std::vector<int64_t> fine_numbering;  // global node -> deal.II dof of comp 0
+  std::vector<double> h_Kell;
+};
+
+namespace {
+
+int fail(const slod_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define NEED_DEVICE()                                                                               \
+  do {                                                                                             \
+    if (ctx->device == SLOD_DEVICE_NONE)                                                           \
+      return fail(ctx, SLOD_ERR_CUDA, "handle was created without a device (maps only); no CPU fallback"); \
+  } while (0)
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, SLOD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+int ipow(int b, int e) {
+  int r = 1;
+  for (int i = 0; i < e; ++i) r *= b;
+  return r;
+}
+
+// Reference sub-cell matrices with the 2-point Gauss rule per axis (QIterated(QGauss<1>(2), n),
+// source/LOD.cc:91-92); local dof = s * (lx + 2 ly + 4 lz) + comp.
+void reference_matrices(Params &P) {
+  const int dim = P.dim, s = P.s, nn = 1 << dim, nl = nn * s;
+  const double h = P.h, g = 0.5 / std::sqrt(3.0);
+  const double pts[2] = {0.5 - g, 0.5 + g};
+  const double jxw = std::pow(h / 2.0, dim);
+  std::fill(P.Kref, P.Kref + kMaxLocal * kMaxLocal, 0.0);
+  std::fill(P.Klam, P.Klam + kMaxLocal * kMaxLocal, 0.0);
+  for (int q = 0; q < nn; ++q) {
+    double x[3] = {pts[q & 1], pts[(q >> 1) & 1], pts[(q >> 2) & 1]};
+    double G[8][3];
+    for (int i = 0; i < nn; ++i) {
+      int nd[3] = {i & 1, (i >> 1) & 1, (i >> 2) & 1};
+      for (int a = 0; a < dim; ++a) {
+        double v = 1.0;
+        for (int b = 0; b < dim; ++b) {
+          if (b == a) v *= (nd[b] ? 1.0 : -1.0) / h;
+          else v *= nd[b] ? x[b] : (1.0 - x[b]);
+        }
+        G[i][a] = v;
+      }
+    }
+    if (P.problem == SLOD_PROBLEM_DIFFUSION) {
+      for (int i = 0; i < nn; ++i)
+        for (int j = 0; j < nn; ++j) {
+          double d = 0;
+          for (int a = 0; a < dim; ++a) d += G[i][a] * G[j][a];
+          P.Kref[i * nl + j] += d * jxw;
+        }
+    } else {
+      // 2 eps(phi_i):eps(phi_j) and div phi_i div phi_j   (include/Elasticity.h:236-250)
+      for (int i = 0; i < nn; ++i)
+        for (int ci = 0; ci < s; ++ci)
+          for (int j = 0; j < nn; ++j)
+            for (int cj = 0; cj < s; ++cj) {
+              double ee = 0.0;
+              for (int a = 0; a < dim; ++a)
+                for (int b = 0; b < dim; ++b) {
+                  const double ei = 0.5 * ((a == ci ? G[i][b] : 0.0) + (b == ci ? G[i][a] : 0.0));
+                  const double ej = 0.5 * ((a == cj ? G[j][b] : 0.0) + (b == cj ? G[j][a] : 0.0));
+                  ee += ei * ej;
+                }
+              P.Kref[(i * s + ci) * nl + (j * s + cj)] += 2.0 * ee * jxw;
+              P.Klam[(i * s + ci) * nl + (j * s + cj)] += G[i][ci] * G[j][cj] * jxw;
+            }
+    }
+  }
+}
+
+// cell-local node multi-indices in deal.II's hierarchical order (vertices, lines, quads, interior)
+std::vector<std::array<int, 3>> cell_walk(int dim, int n) {
+  std::vector<std::array<int, 3>> out;
+  const int e[2] = {0, n};
+  if (dim == 2) {
+    for (int v = 0; v < 4; ++v) out.push_back({e[v & 1], e[(v >> 1) & 1], 0});
+    for (int t = 1; t < n; ++t) out.push_back({0, t, 0});
+    for (int t = 1; t < n; ++t) out.push_back({n, t, 0});
+    for (int t = 1; t < n; ++t) out.push_back({t, 0, 0});
+    for (int t = 1; t < n; ++t) out.push_back({t, n, 0});
+    for (int y = 1; y < n; ++y)
+      for (int x = 1; x < n; ++x) out.push_back({x, y, 0});
+  } else {
+    for (int v = 0; v < 8; ++v) out.push_back({e[v & 1], e[(v >> 1) & 1], e[(v >> 2) & 1]});
+    for (int z = 0; z < 2; ++z) {
+      for (int t = 1; t < n; ++t) out.push_back({0, t, e[z]});
+      for (int t = 1; t < n; ++t) out.push_back({n, t, e[z]});
+      for (int t = 1; t < n; ++t) out.push_back({t, 0, e[z]});
+      for (int t = 1; t < n; ++t) out.push_back({t, n, e[z]});
+    }
+    for (int v = 0; v < 4; ++v)
+      for (int t = 1; t < n; ++t) out.push_back({e[v & 1], e[(v >> 1) & 1], t});
+    for (int f = 0; f < 2; ++f)  // x = 0, x = 1 : free axes y (fast), z
+      for (int z = 1; z < n; ++z)
+        for (int y = 1; y < n; ++y) out.push_back({e[f], y, z});
+    for (int f = 0; f < 2; ++f)  // y faces: free axes x (fast), z
+      for (int z = 1; z < n; ++z)
+        for (int x = 1; x < n; ++x) out.push_back({x, e[f], z});
+    for (int f = 0; f < 2; ++f)  // z faces: free axes x (fast), y
+      for (int y = 1; y < n; ++y)
+        for (int x = 1; x < n; ++x) out.push_back({x, y, e[f]});
+    for (int z = 1; z < n; ++z)
+      for (int y = 1; y < n; ++y)
+        for (int x = 1; x < n; ++x) out.push_back({x, y, z});
+  }
+  return out;
+}
+
+// DoFHandler::distribute_dofs restated: walk `cells`, number unnumbered nodes in hierarchical order
+template <typename CellFn>
+void numbering_walk(int dim, int s, int n, size_t n_cells, CellFn cell_at, const int shape[3], const int origin[3],
+                    std::vector<int64_t> &num) {
+  const auto walk = cell_walk(dim, n);
+  num.assign((size_t)shape[0] * shape[1] * shape[2], -1);
+  int64_t next = 0;
+  for (size_t c = 0; c < n_cells; ++c) {
+    int cc[3];
+    cell_at(c, cc);
+    for (const auto &loc : walk) {
+      const int gx = n * (cc[0] - origin[0]) + loc[0], gy = n * (cc[1] - origin[1]) + loc[1],
+                gz = (dim == 3) ? n * (cc[2] - origin[2]) + loc[2] : 0;
+      int64_t &slot = num[((size_t)gz * shape[1] + gy) * shape[0] + gx];
+      if (slot < 0) {
+        slot = next;
+        next += s;
+      }
+    }
+  }
+}
+
+void patch_cells_rel(const Params &P, const Geom &g, std::vector<std::array<int, 3>> &cells) {
+  cells.resize(g.Nc);
+  for (int pos = 0; pos < g.Nc; ++pos) {
+    int k[3];
+    col_to_cell(P, g, pos, k);
+    cells[pos] = {k[0], k[1], k[2]};
+  }
+}
+
+int check_patch(const slod_ctx *ctx, int64_t patch) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  if (patch < 0 || patch >= ctx->n_patches) return fail(ctx, SLOD_ERR_INVALID, "patch id out of range");
+  return SLOD_OK;
+}
+
+void free_dev(slod_ctx *c) {
+  auto F = [](auto *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
+  F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
+}
+
+int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
+  const Params &P = ctx->P;
+  if (ctx->chunk > 0) return SLOD_OK;
+  const size_t per_patch = ((size_t)ctx->sl.x_stride + 2 * (size_t)ctx->dl.m_stride + (size_t)P.s * P.NcdMax) * 8 + 4;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(budget / per_patch));
+  (void)n_range;
+  chunk = std::min<int64_t>(chunk, ctx->n_patches);
+  ctx->chunk = (int)chunk;
+  CK(cudaMalloc(&ctx->d_ids, sizeof(int) * chunk));
+  CK(cudaMalloc(&ctx->d_X, sizeof(double) * (size_t)ctx->sl.x_stride * chunk));
+  CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
+  CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
+  CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
+  CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
+  return SLOD_OK;
+}
+
+int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_aphi, cudaStream_t st) {
+  const Params &P = ctx->P;
+  for (int f = 0; f < ctx->n_fields; ++f)
+    if (!ctx->coef_set[f]) return fail(ctx, SLOD_ERR_STATE, "coefficient field not set");
+  if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
+  if (p0 == p1) return SLOD_OK;
+  int rc = ensure_workspace(ctx, p1 - p0);
+  if (rc) return rc;
+  CK(upload_params(P));
+  // work order: largest patches first
+  std::vector<int> order((size_t)(p1 - p0));
+  std::iota(order.begin(), order.end(), (int)p0);
+  std::vector<long long> cost(order.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    const Geom g = make_geom(P, order[i]);
+    cost[i] = (long long)g.Ni * g.bw * (g.bw + 4LL * g.Ncd) + (long long)g.Ncd * g.Ncd * g.Ncd * 8;
+  }
+  std::vector<int> perm(order.size());
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<int> ids(order.size());
+  for (size_t i = 0; i < perm.size(); ++i) ids[i] = order[perm[i]];
+
+  float acc[4] = {0, 0, 0, 0};
+  for (size_t off = 0; off < ids.size(); off += ctx->chunk) {
+    const int nw = (int)std::min<size_t>(ctx->chunk, ids.size() - off);
+    CK(cudaMemcpyAsync(ctx->d_ids, ids.data() + off, sizeof(int) * nw, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+                          ctx->d_Lws, ctx->d_status, ctx->sl));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+                          ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(launch_patch_select(std::min(nw, ctx->grid_select), ctx->smem_select, st, ctx->d_ids, nw, ctx->d_Minv,
+                           ctx->d_G, ctx->d_cvec, ctx->d_diag, ctx->d_status, ctx->el));
+    CK(cudaEventRecord(ctx->ev[3], st));
+    CK(launch_patch_finish(std::min(nw, ctx->grid_finish), ctx->smem_finish, st, ctx->d_ids, nw, ctx->d_coef,
+                           ctx->d_X, ctx->d_cvec, d_phi, d_aphi, ctx->fl));
+    CK(cudaEventRecord(ctx->ev[4], st));
+    ctx->launches += 4;
+    CK(cudaEventSynchronize(ctx->ev[4]));  // ids buffer is reused by the next chunk
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));
+      acc[k] += ms;
+    }
+  }
+  for (int k = 0; k < 4; ++k) ctx->tm.ms[k] = acc[k];
+  return SLOD_OK;
+}
+
+int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const double *d_aphi, double *d_K,
+               cudaStream_t st) {
+  if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
+  if (p0 == p1) return SLOD_OK;
+  CK(upload_params(ctx->P));
+  CK(cudaEventRecord(ctx->ev[5], st));
+  CK(launch_coarse((int)std::min<int64_t>(p1 - p0, ctx->grid_coarse), ctx->smem_coarse, st, (int)p0, (int)p1, d_phi,
+                   d_aphi, d_K, ctx->fl));
+  CK(cudaEventRecord(ctx->ev[6], st));
+  ctx->launches += 1;
+  CK(cudaEventSynchronize(ctx->ev[6]));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+  ctx->tm.ms[4] = ms;
+  return SLOD_OK;
+}
+
+// block-ELL -> CSR.  The pattern is integer geometry: (p, q) is structural iff the node boxes intersect.
+int ell_to_csr(const slod_ctx *ctx, const double *hK, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
+               int64_t *nnz) {
+  const Params &P = ctx->P;
+  const int s = P.s, w = P.w, ww = 2 * w + 1;
+  const int nslots = (P.dim == 3) ? ww * ww * ww : ww * ww;
+  const int64_t np = ctx->n_patches;
+  if (n_rows) *n_rows = np * s;
+  // per patch: list of (qid, slot) sorted by qid
+  std::vector<int64_t> cnt((size_t)np + 1, 0);
+  const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  auto neighbours = [&](int64_t pid, std::vector<std::pair<uint32_t, int>> &nb) {
+    nb.clear();
+    const Geom g = make_geom(P, (int)pid);
+    for (int slot = 0; slot < nslots; ++slot) {
+      int D[3] = {slot % ww - w, (slot / ww) % ww - w, (P.dim == 3) ? slot / (ww * ww) - w : 0};
+      int qc[3] = {g.lo[0] + g.cc[0] + D[0], g.lo[1] + g.cc[1] + D[1], g.lo[2] + g.cc[2] + D[2]};
+      bool valid = true;
+      for (int x = 0; x < P.dim; ++x) valid = valid && qc[x] >= 0 && qc[x] < P.N;
+      if (!valid) continue;
+      const uint32_t qid = morton_encode(qc, P.dim, P.ref);
+      const Geom gq = make_geom(P, (int)qid);
+      for (int x = 0; x < P.dim; ++x) {
+        const int b0 = std::max(g.lo[x], gq.lo[x]), b1 = std::min(g.lo[x] + g.m[x], gq.lo[x] + gq.m[x]);
+        if (b1 < b0) valid = false;
+      }
+      if (valid) nb.emplace_back(qid, slot);
+    }
+    std::sort(nb.begin(), nb.end());
+  };
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthr; ++t)
+      th.emplace_back([&, t]() {
+        std::vector<std::pair<uint32_t, int>> nb;
+        for (int64_t pid = t; pid < np; pid += nthr) {
+          neighbours(pid, nb);
+          cnt[pid + 1] = (int64_t)nb.size();
+        }
+      });
+    for (auto &x : th) x.join();
+  }
+  // rows of patch pid: s rows, each nb.size()*s entries
+  std::vector<int64_t> start((size_t)np + 1, 0);
+  for (int64_t p = 0; p < np; ++p) start[p + 1] = start[p] + cnt[p + 1] * s * s;
+  if (nnz) *nnz = start[np];
+  if (!rowptr) return SLOD_OK;
+  if (!col || !val || !hK) return fail(ctx, SLOD_ERR_INVALID, "null output buffer");
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthr; ++t)
+      th.emplace_back([&, t]() {
+        std::vector<std::pair<uint32_t, int>> nb;
+        for (int64_t pid = t; pid < np; pid += nthr) {
+          neighbours(pid, nb);
+          const int64_t per_row = (int64_t)nb.size() * s;
+          for (int d = 0; d < s; ++d) {
+            const int64_t r = pid * s + d;
+            int64_t o = start[pid] + d * per_row;
+            rowptr[r] = o;
+            const double *krow = hK + (size_t)r * P.ell_width;
+            for (const auto &q : nb)
+              for (int e = 0; e < s; ++e) {
+                col[o] = (int64_t)q.first * s + e;
+                val[o] = krow[q.second * s + e];
+                ++o;
+              }
+          }
+        }
+      });
+    for (auto &x : th) x.join();
+  }
+  rowptr[np * s] = start[np];
+  return SLOD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *slod_last_create_error(void) { return g_create_error.c_str(); }
+const char *slod_last_error(const slod_ctx *ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
+
+int slod_create(const slod_params *par, slod_ctx **out) {
+  if (!par || !out) {
+    g_create_error = "null argument";
+    return SLOD_ERR_INVALID;
+  }
+  *out = nullptr;
+  auto bad = [&](int code, const std::string &m) {
+    g_create_error = m;
+    return code;
+  };
+  if (par->dim != 2 && par->dim != 3) return bad(SLOD_ERR_INVALID, "dim must be 2 or 3");
+  if (par->problem == SLOD_PROBLEM_DIFFUSION && par->spacedim != 1)
+    return bad(SLOD_ERR_INVALID, "diffusion needs spacedim 1");
+  if (par->problem == SLOD_PROBLEM_ELASTICITY && (par->spacedim != par->dim || par->dim != 2))
+    return bad(SLOD_ERR_UNSUPPORTED, "elasticity is implemented for dim = spacedim = 2 (as in the reference)");
+  if (par->problem != SLOD_PROBLEM_DIFFUSION && par->problem != SLOD_PROBLEM_ELASTICITY)
+    return bad(SLOD_ERR_INVALID, "unknown problem");
+  if (par->n_global_refinements < 0 || par->n_global_refinements * par->dim > 30)
+    return bad(SLOD_ERR_INVALID, "n_global_refinements out of range");
+  if (par->n_subdivisions < 1 || (par->n_subdivisions & (par->n_subdivisions - 1)))
+    return bad(SLOD_ERR_INVALID, "n_subdivisions must be a power of two (include/Diffusion.h:76-80)");
+  if (par->oversampling < 0) return bad(SLOD_ERR_INVALID, "oversampling < 0");
+
+  // device == SLOD_DEVICE_NONE: integer maps only (patch lists, DoF maps, CSR pattern); every compute
+  // entry point of such a handle fails with SLOD_ERR_CUDA -- there is no CPU fallback.
+  const bool maps_only = (par->device == SLOD_DEVICE_NONE);
+  int dev = par->device;
+  cudaDeviceProp prop{};
+  prop.multiProcessorCount = 148;
+  prop.sharedMemPerBlockOptin = 227 * 1024;
+  prop.sharedMemPerMultiprocessor = 228 * 1024;
+  if (!maps_only) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return bad(SLOD_ERR_CUDA, "no CUDA device: libslod_b200 has no CPU fallback");
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return bad(SLOD_ERR_CUDA, "cudaGetDevice failed");
+    if (dev >= ndev) return bad(SLOD_ERR_INVALID, "device ordinal out of range");
+    if (cudaSetDevice(dev) != cudaSuccess) return bad(SLOD_ERR_CUDA, "cudaSetDevice failed");
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+      return bad(SLOD_ERR_CUDA, "cudaGetDeviceProperties failed");
+  }
+
+  auto *ctx = new slod_ctx();
+  ctx->par = *par;
+  ctx->device = dev;
+  ctx->n_sm = prop.multiProcessorCount;
+  Params &P = ctx->P;
+  P.dim = par->dim; P.s = par->spacedim; P.ref = par->n_global_refinements; P.n = par->n_subdivisions;
+  P.ell = par->oversampling; P.N = 1 << P.ref; P.nsub = P.N * P.n;
+  P.problem = par->problem; P.stabilize = par->stabilize ? 1 : 0; P.quirk_presaved = par->quirk_presaved ? 1 : 0;
+  const int mfull = std::min(2 * P.ell + 1, P.N);
+  P.pmax = P.n * mfull + 1;
+  P.nnodes_max = ipow(P.pmax, P.dim);
+  P.NfMax = P.s * P.nnodes_max;
+  P.NiMax = P.s * ipow(P.pmax - 2, P.dim);
+  P.NcdMax = P.s * ipow(mfull, P.dim);
+  P.w = 2 * P.ell + 1;
+  P.ell_width = ipow(2 * P.w + 1, P.dim) * P.s;
+  P.H = std::ldexp(1.0, -P.ref);
+  P.h = P.H / P.n;
+  P.Hd = std::pow(P.H, P.dim);
+  P.pw = std::pow(P.h, P.dim) / (double)(1 << P.dim);
+  P.has_presaved = 0;
+  ctx->n_patches = (int64_t)ipow(P.N, P.dim);
+  ctx->n_fields = (P.problem == SLOD_PROBLEM_DIFFUSION) ? 1 : 2;
+  reference_matrices(P);
+  // quirk B: the first full-size patch in patch-id order donates its matrix (source/LOD.cc:446-450)
+  {
+    Params Q = P;
+    Q.quirk_presaved = 0;
+    for (int64_t pid = 0; pid < ctx->n_patches; ++pid) {
+      const Geom g = make_geom(Q, (int)pid);
+      if (g.full) {
+        for (int a = 0; a < 3; ++a) P.presaved_lo[a] = g.lo[a];
+        P.has_presaved = 1;
+        break;
+      }
+    }
+  }
+  // maxima over patch shapes
+  int bw_max = 0, nb_max = 0;
+  {
+    // shapes are products of per-axis extents; scanning the patches along the diagonal + full scan for small grids
+    for (int64_t pid = 0; pid < ctx->n_patches; ++pid) {
+      const Geom g = make_geom(P, (int)pid);
+      bw_max = std::max(bw_max, g.bw);
+      int nb = 0;
+      // patch-boundary dofs
+      int cnt_int = 1, cnt_nob = 1;
+      for (int a = 0; a < P.dim; ++a) {
+        cnt_int *= g.p[a];
+        cnt_nob *= g.p[a] - (g.domlo[a] ? 0 : 1) - (g.domhi[a] ? 0 : 1);
+      }
+      nb = P.s * (cnt_int - cnt_nob);
+      nb_max = std::max(nb_max, nb);
+    }
+  }
+  ctx->bw_max = bw_max;
+  ctx->nb_max = nb_max;
+  const bool big = (P.dim == 3);
+  const int msub = P.n * mfull;
+  const int coef_doubles = ctx->n_fields * ipow(msub, P.dim);
+  // ---- layouts ----
+  SolveLayout &sl = ctx->sl;
+  sl.threads = big ? 512 : 128;
+  sl.bw_max = bw_max;
+  sl.R = bw_max + kSolveNB;
+  sl.ldw = bw_max + 1;
+  sl.ldr = P.NcdMax;
+  sl.coef_doubles = coef_doubles;
+  sl.ldx = P.NcdMax;
+  sl.x_stride = (long long)P.NiMax * sl.ldx;
+  const int steps_max = (P.NiMax + kSolveNB - 1) / kSolveNB;
+  sl.lws_per_cta = (long long)steps_max * (kSolveNB * kSolveNB + bw_max * kSolveNB);
+  ctx->smem_solve = sizeof(double) * ((size_t)coef_doubles + (size_t)sl.R * sl.ldw + (size_t)sl.R * sl.ldr +
+                                      (size_t)sl.R * kSolveNB + 2 * kSolveNB * kSolveNB + (size_t)kSolveNB * sl.ldr);
+  DenseLayout &dl = ctx->dl;
+  dl.threads = big ? 512 : 128;
+  dl.ncd_max = P.NcdMax; dl.nb_max = nb_max; dl.coef_doubles = coef_doubles; dl.ldx = sl.ldx;
+  dl.x_stride = sl.x_stride;
+  dl.m_stride = (long long)P.NcdMax * P.NcdMax;
+  ctx->smem_dense = sizeof(double) * ((size_t)coef_doubles + (size_t)dl.m_stride + 2 * 16 * (size_t)P.NcdMax +
+                                      2 * (size_t)P.NcdMax + 16 * 54) +
+                    sizeof(int) * (16 * 54 + (size_t)nb_max + 8);
+  SelectLayout &el = ctx->el;
+  el.threads = big ? 512 : 128;
+  el.ncd_max = P.NcdMax; el.m_stride = dl.m_stride;
+  ctx->smem_select = sizeof(double) * ((size_t)P.NcdMax * (P.NcdMax + 1) / 2 + (size_t)P.NcdMax * P.NcdMax +
+                                       6 * (size_t)P.NcdMax) + sizeof(int) * (3 * (size_t)P.NcdMax + 8);
+  FinishLayout &fl = ctx->fl;
+  fl.coef_doubles = coef_doubles; fl.nf_max = P.NfMax; fl.ncd_max = P.NcdMax; fl.ldx = sl.ldx; fl.x_stride = sl.x_stride;
+  ctx->smem_finish = sizeof(double) * ((size_t)coef_doubles + P.NfMax + P.NcdMax);
+  ctx->smem_coarse = sizeof(double) * ((size_t)P.s * P.NfMax);
+  const size_t smem_cap = prop.sharedMemPerBlockOptin;
+  if ((size_t)P.NcdMax * P.NcdMax > (size_t)32 * dl.threads)
+    { delete ctx; return bad(SLOD_ERR_UNSUPPORTED, "patch too large: coarse dofs per patch exceed the Gram register tile"); }
+  if (ctx->smem_solve > smem_cap || ctx->smem_dense > smem_cap || ctx->smem_select > smem_cap ||
+      ctx->smem_finish > smem_cap || ctx->smem_coarse > smem_cap) {
+    delete ctx;
+    return bad(SLOD_ERR_UNSUPPORTED, "patch too large for the shared-memory resident solver (oversampling/subdivisions)");
+  }
+  auto per_sm = [&](size_t smem, int threads) {
+    int by_smem = (int)std::max<size_t>(1, (prop.sharedMemPerMultiprocessor) / (smem + 1024));
+    int by_thr = std::max(1, 2048 / threads);
+    return std::max(1, std::min(std::min(by_smem, by_thr), 16));
+  };
+  ctx->grid_solve = ctx->n_sm * per_sm(ctx->smem_solve, sl.threads);
+  ctx->grid_dense = ctx->n_sm * per_sm(ctx->smem_dense, dl.threads);
+  ctx->grid_select = ctx->n_sm * per_sm(ctx->smem_select, el.threads);
+  ctx->grid_finish = ctx->n_sm * per_sm(ctx->smem_finish, 256);
+  ctx->grid_coarse = ctx->n_sm * per_sm(ctx->smem_coarse, 256);
+
+  auto cuda_bad = [&](const char *what, cudaError_t e) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    free_dev(ctx);
+    delete ctx;
+    return SLOD_ERR_CUDA;
+  };
+  cudaError_t e;
+  ctx->coef_field_elems = (size_t)ipow(P.nsub, P.dim);
+  if (maps_only) {
+    *out = ctx;
+    return SLOD_OK;
+  }
+  if ((e = cudaMalloc(&ctx->d_coef, sizeof(double) * ctx->coef_field_elems * ctx->n_fields)) != cudaSuccess)
+    return cuda_bad("cudaMalloc coef", e);
+  if ((e = cudaMalloc(&ctx->d_status, sizeof(int) * ctx->n_patches)) != cudaSuccess) return cuda_bad("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->d_diag, sizeof(double) * 8 * P.s * ctx->n_patches)) != cudaSuccess)
+    return cuda_bad("cudaMalloc", e);
+  cudaMemset(ctx->d_status, 0, sizeof(int) * ctx->n_patches);
+  cudaMemset(ctx->d_diag, 0, sizeof(double) * 8 * P.s * ctx->n_patches);
+  for (auto &ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_bad("cudaEventCreate", e);
+  *out = ctx;
+  return SLOD_OK;
+}
+
+void slod_destroy(slod_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->device == SLOD_DEVICE_NONE) {
+    delete ctx;
+    return;
+  }
+  cudaSetDevice(ctx->device);
+  free_dev(ctx);
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete ctx;
+}
+
+int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const double *cellwise, size_t n) {
+  if (!ctx || !cellwise) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  const Params &P = ctx->P;
+  if (field < 0 || field >= ctx->n_fields) return fail(ctx, SLOD_ERR_INVALID, "coefficient field index out of range");
+  if (eta_refinement < 0 || eta_refinement > 15) return fail(ctx, SLOD_ERR_INVALID, "eta_refinement out of range");
+  const int nl = 1 << eta_refinement;
+  if ((size_t)ipow(nl, P.dim) != n) return fail(ctx, SLOD_ERR_INVALID, "coefficient table size != (2^r)^dim");
+  if (nl > P.nsub)
+    return fail(ctx, SLOD_ERR_UNSUPPORTED,
+                "coefficient grid finer than the fine sub-cells (eta < h): not constant per sub-cell");
+  const int ratio = P.nsub / nl;  // power of two
+  std::vector<double> fine(ctx->coef_field_elems);
+  const int ns = P.nsub;
+  const int nz = (P.dim == 3) ? ns : 1;
+  for (int z = 0; z < nz; ++z)
+    for (int y = 0; y < ns; ++y)
+      for (int x = 0; x < ns; ++x)
+        fine[((size_t)z * ns + y) * ns + x] = cellwise[((size_t)(z / ratio) * nl + (y / ratio)) * nl + (x / ratio)];
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(ctx->d_coef + (size_t)field * ctx->coef_field_elems, fine.data(), sizeof(double) * fine.size(),
+                cudaMemcpyHostToDevice));
+  ctx->coef_set[field] = true;
+  ctx->basis_done = ctx->coarse_done = false;
+  return SLOD_OK;
+}
+
+int slod_patch_count(const slod_ctx *ctx, int64_t *n) {
+  if (!ctx || !n) return SLOD_ERR_INVALID;
+  *n = ctx->n_patches;
+  return SLOD_OK;
+}
+
+int slod_get_patch_info(const slod_ctx *ctx, int64_t patch, int32_t *n_cells, int32_t *n_fine, int32_t *n_internal,
+                        int32_t *n_boundary, int32_t *n_domain_boundary, int32_t *n_coarse, int32_t lo[3],
+                        int32_t m[3]) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  const Params &P = ctx->P;
+  const Geom g = make_geom(P, (int)patch);
+  int nb = 0, ndb = 0;
+  for (int node = 0; node < g.nnodes; ++node) {
+    int a[3];
+    node_coords(g, node, a);
+    const int c = node_class(P, g, a);
+    nb += (c & 1) ? P.s : 0;
+    ndb += (c & 2) ? P.s : 0;
+  }
+  if (n_cells) *n_cells = g.Nc;
+  if (n_fine) *n_fine = g.Nf;
+  if (n_internal) *n_internal = g.Ni;
+  if (n_boundary) *n_boundary = nb;
+  if (n_domain_boundary) *n_domain_boundary = ndb;
+  if (n_coarse) *n_coarse = g.Ncd;
+  for (int a = 0; a < 3; ++a) {
+    if (lo) lo[a] = g.lo[a];
+    if (m) m[a] = g.m[a];
+  }
+  return SLOD_OK;
+}
+
+int slod_get_patch_cells(const slod_ctx *ctx, int64_t patch, uint32_t *cells, int32_t *n) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  const Params &P = ctx->P;
+  const Geom g = make_geom(P, (int)patch);
+  if (n) *n = g.Nc;
+  if (!cells) return SLOD_OK;
+  for (int pos = 0; pos < g.Nc; ++pos) {
+    int k[3];
+    col_to_cell(P, g, pos, k);
+    int c[3] = {g.lo[0] + k[0], g.lo[1] + k[1], g.lo[2] + k[2]};
+    cells[pos] = morton_encode(c, P.dim, P.ref);
+  }
+  return SLOD_OK;
+}
+
+int slod_get_patch_fine_dofs(const slod_ctx *ctx, int64_t patch, uint64_t *dofs, int32_t *n) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  const Params &P = ctx->P;
+  const Geom g = make_geom(P, (int)patch);
+  if (n) *n = g.Nf;
+  if (!dofs) return SLOD_OK;
+  const int G = P.nsub + 1;
+  if (ctx->fine_numbering.empty()) {
+    const int shape[3] = {G, G, P.dim == 3 ? G : 1};
+    const int origin[3] = {0, 0, 0};
+    numbering_walk(P.dim, P.s, P.n, (size_t)ctx->n_patches,
+                   [&](size_t c, int cc[3]) { morton_decode((uint32_t)c, P.dim, P.ref, cc); }, shape, origin,
+                   ctx->fine_numbering);
+  }
+  for (int node = 0; node < g.nnodes; ++node) {
+    int a[3];
+    node_coords(g, node, a);
+    const size_t gx = (size_t)g.lo[0] * P.n + a[0], gy = (size_t)g.lo[1] * P.n + a[1],
+                 gz = (P.dim == 3) ? (size_t)g.lo[2] * P.n + a[2] : 0;
+    const int64_t base = ctx->fine_numbering[(gz * G + gy) * G + gx];
+    for (int c = 0; c < P.s; ++c) dofs[(size_t)node * P.s + c] = (uint64_t)(base + c);
+  }
+  return SLOD_OK;
+}
+
+int slod_get_patch_local_dofs(const slod_ctx *ctx, int64_t patch, uint32_t *dofs, int32_t *n) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  const Params &P = ctx->P;
+  const Geom g = make_geom(P, (int)patch);
+  if (n) *n = g.Nf;
+  if (!dofs) return SLOD_OK;
+  std::vector<std::array<int, 3>> cells;
+  patch_cells_rel(P, g, cells);
+  std::vector<int64_t> num;
+  const int shape[3] = {g.p[0], g.p[1], g.p[2]};
+  const int origin[3] = {0, 0, 0};
+  numbering_walk(P.dim, P.s, P.n, cells.size(),
+                 [&](size_t c, int cc[3]) { cc[0] = cells[c][0]; cc[1] = cells[c][1]; cc[2] = cells[c][2]; }, shape,
+                 origin, num);
+  for (int node = 0; node < g.nnodes; ++node)
+    for (int c = 0; c < P.s; ++c) dofs[(size_t)node * P.s + c] = (uint32_t)(num[node] + c);
+  return SLOD_OK;
+}
+
+int slod_get_patch_dof_class(const slod_ctx *ctx, int64_t patch, int which, uint32_t *dofs, int32_t *n) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  if (which < 0 || which > 2) return fail(ctx, SLOD_ERR_INVALID, "which must be 0, 1 or 2");
+  const Params &P = ctx->P;
+  const Geom g = make_geom(P, (int)patch);
+  int cnt = 0;
+  for (int node = 0; node < g.nnodes; ++node) {
+    int a[3];
+    node_coords(g, node, a);
+    const int c = node_class(P, g, a);
+    const bool in = (which == 0) ? (c == 0) : (which == 1 ? (c & 1) : (c & 2));
+    if (!in) continue;
+    for (int k = 0; k < P.s; ++k) {
+      if (dofs) dofs[cnt] = (uint32_t)(node * P.s + k);
+      ++cnt;
+    }
+  }
+  if (n) *n = cnt;
+  return SLOD_OK;
+}
+
+int slod_basis_stride(const slod_ctx *ctx, int64_t *stride) {
+  if (!ctx || !stride) return SLOD_ERR_INVALID;
+  *stride = ctx->P.NfMax;
+  return SLOD_OK;
+}
+int slod_ell_width(const slod_ctx *ctx, int64_t *width) {
+  if (!ctx || !width) return SLOD_ERR_INVALID;
+  *width = ctx->P.ell_width;
+  return SLOD_OK;
+}
+int slod_launch_count(const slod_ctx *ctx, int64_t *n) {
+  if (!ctx || !n) return SLOD_ERR_INVALID;
+  *n = ctx->launches;
+  return SLOD_OK;
+}
+
+int slod_compute_basis_device(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_aphi, void *stream) {
+  if (!ctx || !d_phi || !d_aphi) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  return run_basis(ctx, p0, p1, d_phi, d_aphi, (cudaStream_t)stream);
+}
+
+int slod_assemble_coarse_device(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const double *d_aphi,
+                                double *d_K, void *stream) {
+  if (!ctx || !d_phi || !d_aphi || !d_K) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  return run_coarse(ctx, p0, p1, d_phi, d_aphi, d_K, (cudaStream_t)stream);
+}
+
+int slod_compute_basis(slod_ctx *ctx) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax;
+  if (!ctx->d_phi) {
+    CK(cudaMalloc(&ctx->d_phi, sizeof(double) * n));
+    CK(cudaMalloc(&ctx->d_aphi, sizeof(double) * n));
+  }
+  CK(cudaMemset(ctx->d_status, 0, sizeof(int) * ctx->n_patches));
+  int rc = run_basis(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, 0);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  std::vector<int> st((size_t)ctx->n_patches);
+  CK(cudaMemcpy(st.data(), ctx->d_status, sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
+  ctx->basis_done = true;
+  ctx->coarse_done = false;
+  for (size_t i = 0; i < st.size(); ++i)
+    if (st[i]) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "patch %zu: numerical status bits 0x%x (1 A_ii not SPD, 2 M not SPD, 4 Jacobi not converged)",
+               i, st[i]);
+      return fail(ctx, SLOD_ERR_NUMERIC, buf);
+    }
+  return SLOD_OK;
+}
+
+int slod_get_basis(const slod_ctx *ctx, int64_t patch, int comp, double *phi, double *aphi) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  if (comp < 0 || comp >= ctx->P.s) return fail(ctx, SLOD_ERR_INVALID, "component out of range");
+  const Geom g = make_geom(ctx->P, (int)patch);
+  const size_t off = ((size_t)patch * ctx->P.s + comp) * ctx->P.NfMax;
+  CK(cudaSetDevice(ctx->device));
+  if (phi) CK(cudaMemcpy(phi, ctx->d_phi + off, sizeof(double) * g.Nf, cudaMemcpyDeviceToHost));
+  if (aphi) CK(cudaMemcpy(aphi, ctx->d_aphi + off, sizeof(double) * g.Nf, cudaMemcpyDeviceToHost));
+  return SLOD_OK;
+}
+
+int slod_get_all_basis(const slod_ctx *ctx, double *phi, double *aphi) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax;
+  CK(cudaSetDevice(ctx->device));
+  if (phi) CK(cudaMemcpy(phi, ctx->d_phi, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (aphi) CK(cudaMemcpy(aphi, ctx->d_aphi, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return SLOD_OK;
+}
+
+int slod_assemble_coarse(slod_ctx *ctx) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.ell_width;
+  if (!ctx->d_Kell) CK(cudaMalloc(&ctx->d_Kell, sizeof(double) * n));
+  int rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0);
+  if (rc) return rc;
+  ctx->h_Kell.resize(n);
+  CK(cudaMemcpy(ctx->h_Kell.data(), ctx->d_Kell, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  ctx->coarse_done = true;
+  return SLOD_OK;
+}
+
+int slod_get_coarse_csr(const slod_ctx *ctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
+                        int64_t *nnz) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  if (rowptr && !ctx->coarse_done) return fail(ctx, SLOD_ERR_STATE, "slod_assemble_coarse has not run");
+  return ell_to_csr(ctx, ctx->h_Kell.data(), rowptr, col, val, n_rows, nnz);
+}
+
+int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,
+                    int64_t *n_rows, int64_t *nnz) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  return ell_to_csr(ctx, h_K, rowptr, col, val, n_rows, nnz);
+}
+
+int slod_get_patch_diagnostics(const slod_ctx *ctx, int64_t patch, int comp, double out[8]) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  NEED_DEVICE();
+  if (!out || comp < 0 || comp >= ctx->P.s) return fail(ctx, SLOD_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(out, ctx->d_diag + ((size_t)patch * ctx->P.s + comp) * 8, sizeof(double) * 8, cudaMemcpyDeviceToHost));
+  int st = 0;
+  CK(cudaMemcpy(&st, ctx->d_status + patch, sizeof(int), cudaMemcpyDeviceToHost));
+  out[7] = st;
+  return SLOD_OK;
+}
+
+int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Minv, double *G) {
+  int rc = check_patch(ctx, patch);
+  if (rc) return rc;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  for (int f = 0; f < ctx->n_fields; ++f)
+    if (!ctx->coef_set[f]) return fail(ctx, SLOD_ERR_STATE, "coefficient field not set");
+  rc = ensure_workspace(ctx, 1);
+  if (rc) return rc;
+  CK(upload_params(ctx->P));
+  const int id = (int)patch;
+  CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
+  CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
+  CK(launch_patch_dense(1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag,
+                        ctx->d_status, ctx->dl));
+  ctx->launches += 2;
+  CK(cudaDeviceSynchronize());
+  const Geom g = make_geom(ctx->P, id);
+  if (X) CK(cudaMemcpy2D(X, sizeof(double) * g.Ncd, ctx->d_X, sizeof(double) * ctx->sl.ldx, sizeof(double) * g.Ncd, g.Ni,
+                         cudaMemcpyDeviceToHost));
+  if (Minv) CK(cudaMemcpy(Minv, ctx->d_Minv, sizeof(double) * g.Ncd * g.Ncd, cudaMemcpyDeviceToHost));
+  if (G) {
+    if (!g.slod) return fail(ctx, SLOD_ERR_STATE, "patch takes the LOD branch: no Gram matrix");
+    CK(cudaMemcpy(G, ctx->d_G, sizeof(double) * g.Ncd * g.Ncd, cudaMemcpyDeviceToHost));
+  }
+  return SLOD_OK;
+}
+
+int slod_get_timings(const slod_ctx *ctx, double *ms, int n) {
+  if (!ctx || !ms) return SLOD_ERR_INVALID;
+  for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->tm.ms[i];
+  return SLOD_OK;
+}
+
+}  // extern "C"

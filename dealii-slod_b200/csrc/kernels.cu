@@ -1,0 +1,853 @@
+// sm_100a kernels of the SLOD offline phase.  One CTA owns one patch at a time; the reference's
+// per-patch loop (source/LOD.cc:345-767) becomes five batched kernels:
+//
+//   k_patch_solve   assemble A_ii (band) + P_i on the fly, blocked banded Cholesky with the multi-RHS
+//                   forward substitution fused in, then the backward substitution  -> X = A_ii^{-1} P_i
+//                   (replaces assemble_stiffness + Gauss_elimination, source/LOD.cc:433-546)
+//   k_patch_dense   M = P^T X / H^d, M^{-1} (in-place Gauss-Jordan like FullMatrix::gauss_jordan),
+//                   BD = (S_b X - P_b) M^{-1} streamed in row tiles, G = BD^T BD   (source/LOD.cc:548-553, 609-618, 660)
+//   k_patch_select  per component: thresholded pseudo-inverse of G[o,o] by a cyclic Jacobi eigen-solver,
+//                   truncation loop, c = M^{-1}(e_d + sum d_k e_k)                  (source/LOD.cc:620-743)
+//   k_patch_finish  phi = X c, zero extension, normalisation, A phi                  (source/LOD.cc:745-765)
+//   k_coarse        K[(p,d),(q,e)] = phi_{p,d} . (A phi)_{q,e} over shared fine nodes (source/LOD.cc:860-973)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "geom.h"
+#include "kernels.h"
+
+namespace slod {
+
+__constant__ Params cP;
+
+cudaError_t upload_params(const Params &p) { return cudaMemcpyToSymbol(cP, &p, sizeof(Params)); }
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nfields() { return cP.problem == 0 ? 1 : 2; }
+
+// copy the patch's sub-cell coefficients (window origin g.clo) into shared memory, field-major
+__device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, double *sCoef) {
+  const int n = cP.n;
+  const int msx = g.m[0] * n, msy = g.m[1] * n, msz = (cP.dim == 3) ? g.m[2] * n : 1;
+  const int nsubp = msx * msy * msz;
+  const long long nsub = cP.nsub;
+  const long long fstride = (cP.dim == 3) ? nsub * nsub * nsub : nsub * nsub;
+  const int nf = nfields();
+  for (int idx = threadIdx.x; idx < nf * nsubp; idx += blockDim.x) {
+    const int f = idx / nsubp;
+    int r = idx - f * nsubp;
+    const int ox = r % msx;
+    r /= msx;
+    const int oy = r % msy;
+    const int oz = r / msy;
+    const long long gx = (long long)g.clo[0] * n + ox, gy = (long long)g.clo[1] * n + oy,
+                    gz = (cP.dim == 3) ? (long long)g.clo[2] * n + oz : 0;
+    sCoef[idx] = d_coef[f * fstride + (gz * nsub + gy) * nsub + gx];
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// interior dof r -> node coords + component
+__device__ __forceinline__ void idof_to_node(const Geom &g, int r, int a[3], int &comp) {
+  comp = r % cP.s;
+  interior_coords(g, r / cP.s, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_patch_solve
+// ------------------------------------------------------------------------------------------------
+// Shared-memory plan (doubles): coef | W band window [R][ldw] | RHS window [R][ldr] | Lp [R][NB] |
+// Ld [NB][NB] | Linv [NB][NB] | Yd [NB][ldr]
+template <int NB>
+__global__ void __launch_bounds__(512, 1)
+k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
+              double *__restrict__ Xbuf, double *__restrict__ Lws, int *__restrict__ status, SolveLayout lay) {
+  extern __shared__ double smem[];
+  double *sCoef = smem;
+  double *sW = sCoef + lay.coef_doubles;
+  double *sR = sW + (size_t)lay.R * lay.ldw;
+  double *sLp = sR + (size_t)lay.R * lay.ldr;
+  double *sLd = sLp + (size_t)lay.R * NB;
+  double *sLinv = sLd + NB * NB;
+  double *sYd = sLinv + NB * NB;
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int R = lay.R, ldw = lay.ldw, ldr = lay.ldr;
+  double *myL = Lws + (size_t)blockIdx.x * lay.lws_per_cta;
+  const int lstep = NB * NB + lay.bw_max * NB;  // doubles per panel in the L workspace
+
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pid = patch_ids[w];
+    const Geom g = make_geom(cP, pid);
+    const int Ni = g.Ni, bw = g.bw, ncd = g.Ncd;
+    double *X = Xbuf + (size_t)w * lay.x_stride;
+    __syncthreads();
+    load_coef(g, d_coef, sCoef);
+    __syncthreads();
+
+    // assemble rows [r0, r1) of the band of A_ii and of P_i into the windows
+    auto assemble_rows = [&](int r0, int r1) {
+      if (r1 > Ni) r1 = Ni;
+      if (r0 >= r1) return;
+      const int nr = r1 - r0;
+      // zero the band rows
+      for (int idx = tid; idx < nr * (bw + 1); idx += NT) {
+        const int r = r0 + idx / (bw + 1);
+        sW[(r % R) * ldw + idx % (bw + 1)] = 0.0;
+      }
+      // right-hand side P_i (dense row of length ncd)
+      for (int idx = tid; idx < nr * ncd; idx += NT) {
+        const int r = r0 + idx / ncd, col = idx % ncd;
+        int a[3], ca;
+        idof_to_node(g, r, a, ca);
+        sR[(r % R) * ldr + col] = proj_entry(cP, g, a, ca, col);
+      }
+    };
+    auto assemble_band = [&](int r0, int r1) {
+      if (r1 > Ni) r1 = Ni;
+      if (r0 >= r1) return;
+      const int nr = r1 - r0;
+      const int nst = (cP.dim == 3) ? 27 : 9;
+      const int per_row = nst * cP.s;
+      for (int idx = tid; idx < nr * per_row; idx += NT) {
+        const int r = r0 + idx / per_row;
+        int e = idx % per_row;
+        const int cb = e % cP.s;
+        e /= cP.s;
+        int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
+        int a[3], ca;
+        idof_to_node(g, r, a, ca);
+        int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
+        bool inside = true;
+        for (int x = 0; x < cP.dim; ++x) inside = inside && (b[x] >= 1 && b[x] <= g.p[x] - 2);
+        if (!inside) continue;
+        const int c = interior_index(g, b) * cP.s + cb;
+        if (c > r) continue;
+        sW[(r % R) * ldw + (c - r + bw)] = stiff_entry(cP, g, sCoef, a, dl, ca, cb);
+      }
+    };
+
+    assemble_rows(0, NB + bw);
+    __syncthreads();
+    assemble_band(0, NB + bw);
+    __syncthreads();
+
+    int bad = 0;
+    // ---------------- factorisation + forward substitution ----------------
+    for (int c0 = 0, step = 0; c0 < Ni; c0 += NB, ++step) {
+      const int nb = min(NB, Ni - c0);
+      const int r1 = min(Ni, c0 + nb + bw);
+      const int npr = r1 - (c0 + nb);
+      if (warp == 0) {
+        for (int idx = lane; idx < NB * NB; idx += 32) {
+          const int i = idx / NB, j = idx % NB;
+          double v = 0.0;
+          if (i < nb && j <= i) v = sW[((c0 + i) % R) * ldw + (j - i + bw)];
+          sLd[idx] = v;
+          sLinv[idx] = 0.0;
+        }
+        __syncwarp();
+        for (int k = 0; k < nb; ++k) {
+          const double dkk = sLd[k * NB + k];
+          if (!(dkk > 0.0)) bad = 1;
+          const double dk = sqrt(dkk);
+          __syncwarp();
+          if (lane == 0) sLd[k * NB + k] = dk;
+          if (lane > k && lane < nb) sLd[lane * NB + k] /= dk;
+          __syncwarp();
+          for (int idx = lane; idx < nb * nb; idx += 32) {
+            const int i = idx / nb, j = idx % nb;
+            if (j > k && j <= i) sLd[i * NB + j] -= sLd[i * NB + k] * sLd[j * NB + k];
+          }
+          __syncwarp();
+        }
+        if (lane < nb) {  // column `lane` of L_D^{-1}
+          const int j = lane;
+          double x[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            if (i >= j && i < nb) {
+              double sum = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+              for (int t = 0; t < NB; ++t)
+                if (t >= j && t < i) sum -= sLd[i * NB + t] * x[t];
+              x[i] = sum / sLd[i * NB + i];
+              sLinv[i * NB + j] = x[i];
+            } else {
+              x[i] = 0.0;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // panel  Lp = W[panel rows, c0:c0+nb] * L_D^{-T}
+      for (int idx = tid; idx < npr * NB; idx += NT) {
+        const int r = idx / NB, k = idx % NB;
+        const int i = c0 + nb + r;
+        double acc = 0.0;
+        if (k < nb) {
+          for (int t = 0; t <= k; ++t) {
+            const int c = c0 + t;
+            if (i - c <= bw) acc += sW[(i % R) * ldw + (c - i + bw)] * sLinv[k * NB + t];
+          }
+        }
+        sLp[idx] = acc;
+      }
+      // Y_D = L_D^{-1} R_D
+      for (int idx = tid; idx < NB * ncd; idx += NT) {
+        const int k = idx / ncd, col = idx % ncd;
+        double acc = 0.0;
+        if (k < nb)
+          for (int t = 0; t <= k; ++t) acc += sLinv[k * NB + t] * sR[((c0 + t) % R) * ldr + col];
+        sYd[k * ldr + col] = acc;
+      }
+      __syncthreads();
+      // trailing update of the band window
+      for (int idx = tid; idx < npr * npr; idx += NT) {
+        const int ri = idx / npr, rj = idx % npr;
+        if (rj > ri) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += sLp[ri * NB + k] * sLp[rj * NB + k];
+        const int i = c0 + nb + ri, j = c0 + nb + rj;
+        sW[(i % R) * ldw + (j - i + bw)] -= acc;
+      }
+      // right-hand side update
+      for (int idx = tid; idx < npr * ncd; idx += NT) {
+        const int r = idx / ncd, col = idx % ncd;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += sLp[r * NB + k] * sYd[k * ldr + col];
+        sR[((c0 + nb + r) % R) * ldr + col] -= acc;
+      }
+      // spill the panel for the backward substitution, Y_D to X
+      {
+        double *Ls = myL + (size_t)step * lstep;
+        for (int idx = tid; idx < NB * NB; idx += NT) Ls[idx] = sLinv[idx];
+        for (int idx = tid; idx < npr * NB; idx += NT) Ls[NB * NB + idx] = sLp[idx];
+        for (int idx = tid; idx < nb * ncd; idx += NT) {
+          const int k = idx / ncd, col = idx % ncd;
+          X[(size_t)(c0 + k) * lay.ldx + col] = sYd[k * ldr + col];
+        }
+      }
+      // slide the window: rows [c0+nb+bw, c0+2nb+bw) take the slots of rows [c0, c0+nb)
+      assemble_rows(c0 + nb + bw, c0 + 2 * nb + bw);
+      __syncthreads();
+      assemble_band(c0 + nb + bw, c0 + 2 * nb + bw);
+      __syncthreads();
+    }
+    if (bad && tid == 0) atomicOr(&status[pid], 1);
+
+    // ---------------- backward substitution:  L^T X = Y ----------------
+    const int last = ((Ni - 1) / NB) * NB;
+    for (int c0 = last, step = last / NB; c0 >= 0; c0 -= NB, --step) {
+      const int nb = min(NB, Ni - c0);
+      const int r1 = min(Ni, c0 + nb + bw);
+      const int npr = r1 - (c0 + nb);
+      const double *Ls = myL + (size_t)step * lstep;
+      for (int idx = tid; idx < NB * NB; idx += NT) sLinv[idx] = Ls[idx];
+      for (int idx = tid; idx < npr * NB; idx += NT) sLp[idx] = Ls[NB * NB + idx];
+      for (int idx = tid; idx < NB * ncd; idx += NT) {
+        const int k = idx / ncd, col = idx % ncd;
+        sYd[k * ldr + col] = (k < nb) ? X[(size_t)(c0 + k) * lay.ldx + col] : 0.0;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nb * ncd; idx += NT) {
+        const int k = idx / ncd, col = idx % ncd;
+        double acc = sYd[k * ldr + col];
+        for (int r = 0; r < npr; ++r) acc -= sLp[r * NB + k] * sR[((c0 + nb + r) % R) * ldr + col];
+        sYd[k * ldr + col] = acc;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nb * ncd; idx += NT) {
+        const int k = idx / ncd, col = idx % ncd;
+        double acc = 0.0;
+        for (int t = k; t < nb; ++t) acc += sLinv[t * NB + k] * sYd[t * ldr + col];
+        sR[((c0 + k) % R) * ldr + col] = acc;
+        X[(size_t)(c0 + k) * lay.ldx + col] = acc;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_patch_dense
+// ------------------------------------------------------------------------------------------------
+constexpr int kTB = 16;      // boundary rows per tile
+constexpr int kGEPT = 32;    // Gram entries per thread (Ncd^2 <= kGEPT * blockDim)
+
+__global__ void __launch_bounds__(512, 1)
+k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
+              const double *__restrict__ Xbuf, double *__restrict__ Minv_out, double *__restrict__ G_out,
+              double *__restrict__ diag, int *__restrict__ status, DenseLayout lay) {
+  extern __shared__ double smem[];
+  double *sCoef = smem;
+  double *sM = sCoef + lay.coef_doubles;                 // [ncd][ncd]
+  double *sT1 = sM + (size_t)lay.ncd_max * lay.ncd_max;  // [kTB][ncd]  W tile
+  double *sT2 = sT1 + kTB * lay.ncd_max;                 // [kTB][ncd]  BD tile
+  double *sCol = sT2 + kTB * lay.ncd_max;                // [ncd] pivot column
+  double *sRow = sCol + lay.ncd_max;                     // [ncd] pivot row
+  double *sArow = sRow + lay.ncd_max;                    // [kTB][27*s] stencil row entries
+  int *sAnbr = (int *)(sArow + kTB * 27 * 2);            // [kTB][27*s] interior dof of the neighbour or -1
+  int *sBlist = sAnbr + kTB * 27 * 2;                    // [NbMax] boundary dofs
+  __shared__ int sNb;
+  __shared__ double sPiv[2];
+  const int tid = threadIdx.x, NT = blockDim.x;
+
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pid = patch_ids[w];
+    const Geom g = make_geom(cP, pid);
+    const int ncd = g.Ncd, s = cP.s;
+    const double *X = Xbuf + (size_t)w * lay.x_stride;
+    __syncthreads();
+    load_coef(g, d_coef, sCoef);
+    if (tid == 0) { sNb = 0; sPiv[0] = 0.0; sPiv[1] = 1e300; }
+    __syncthreads();
+
+    // ---- M = P_i^T X / H^d  (source/LOD.cc:548-551); P is the cell-wise weight stencil ----
+    const int npc = cP.n + 1;
+    const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;
+    const double scale = cP.pw / cP.Hd;
+    for (int idx = tid; idx < ncd * ncd; idx += NT) {
+      const int row = idx / ncd, col = idx % ncd;
+      const int comp = row % s;
+      int k[3];
+      col_to_cell(cP, g, row / s, k);
+      double acc = 0.0;
+      for (int l = 0; l < nloc; ++l) {
+        int t[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
+        int a[3] = {k[0] * cP.n + t[0], k[1] * cP.n + t[1], (cP.dim == 3) ? k[2] * cP.n + t[2] : 0};
+        if (node_class(cP, g, a) != 0) continue;
+        double wgt = 1.0;
+        for (int x = 0; x < cP.dim; ++x)
+          if (t[x] != 0 && t[x] != cP.n) wgt *= 2.0;
+        acc += wgt * X[(size_t)(interior_index(g, a) * s + comp) * lay.ldx + col];
+      }
+      sM[row * ncd + col] = acc * scale;
+    }
+    // boundary dof list (order irrelevant for BD^T BD)
+    if (g.slod) {
+      for (int node = tid; node < g.nnodes; node += NT) {
+        int a[3];
+        node_coords(g, node, a);
+        if (node_class(cP, g, a) & 1) {
+          const int pos = atomicAdd(&sNb, s);
+          for (int c = 0; c < s; ++c) sBlist[pos + c] = node * s + c;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- M^{-1} by in-place Gauss-Jordan sweeps (FullMatrix::gauss_jordan, source/LOD.cc:553) ----
+    for (int k = 0; k < ncd; ++k) {
+      const double piv = sM[k * ncd + k];
+      for (int j = tid; j < ncd; j += NT) {
+        sCol[j] = sM[j * ncd + k];
+        sRow[j] = sM[k * ncd + j] / piv;
+      }
+      if (tid == 0) {
+        if (!(piv > 0.0)) atomicOr(&status[pid], 2);
+      }
+      __syncthreads();
+      for (int idx = tid; idx < ncd * ncd; idx += NT) {
+        const int i = idx / ncd, j = idx % ncd;
+        double v;
+        if (i == k && j == k) v = 1.0 / piv;
+        else if (i == k) v = sRow[j];
+        else if (j == k) v = -sCol[i] / piv;
+        else v = sM[idx] - sCol[i] * sRow[j];
+        sM[idx] = v;
+      }
+      __syncthreads();
+    }
+    {
+      double *Mo = Minv_out + (size_t)w * lay.m_stride;
+      for (int idx = tid; idx < ncd * ncd; idx += NT) Mo[idx] = sM[idx];
+    }
+    if (!g.slod) continue;
+
+    // ---- BD = (S_b X_i - P_b) M^{-1} in tiles of kTB boundary rows; G += BD^T BD ----
+    double gacc[kGEPT];
+#pragma unroll
+    for (int e = 0; e < kGEPT; ++e) gacc[e] = 0.0;
+    const int nbd = sNb;
+    const int nst = (cP.dim == 3) ? 27 : 9;
+    const int per_row = nst * s;
+    for (int t0 = 0; t0 < nbd; t0 += kTB) {
+      const int nt = min(kTB, nbd - t0);
+      // stencil entries of the boundary rows towards interior dofs
+      for (int idx = tid; idx < nt * per_row; idx += NT) {
+        const int rb = idx / per_row;
+        int e = idx % per_row;
+        const int cb = e % s;
+        e /= s;
+        int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
+        const int dof = sBlist[t0 + rb];
+        int a[3];
+        node_coords(g, dof / s, a);
+        int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
+        bool ok = true;
+        for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 1 && b[x] <= g.p[x] - 2);
+        if (ok) {
+          sAnbr[idx] = interior_index(g, b) * s + cb;
+          sArow[idx] = stiff_entry(cP, g, sCoef, a, dl, dof % s, cb);
+        } else {
+          sAnbr[idx] = -1;
+          sArow[idx] = 0.0;
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nt * ncd; idx += NT) {
+        const int rb = idx / ncd, col = idx % ncd;
+        const int dof = sBlist[t0 + rb];
+        int a[3];
+        node_coords(g, dof / s, a);
+        double acc = -proj_entry(cP, g, a, dof % s, col);
+        for (int e = 0; e < per_row; ++e) {
+          const int nb_ = sAnbr[rb * per_row + e];
+          if (nb_ >= 0) acc += sArow[rb * per_row + e] * X[(size_t)nb_ * lay.ldx + col];
+        }
+        sT1[rb * ncd + col] = acc;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < nt * ncd; idx += NT) {
+        const int rb = idx / ncd, col = idx % ncd;
+        double acc = 0.0;
+        for (int k = 0; k < ncd; ++k) acc += sT1[rb * ncd + k] * sM[k * ncd + col];
+        sT2[idx] = acc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < kGEPT; ++e) {
+        const int idx = tid + e * NT;
+        if (idx < ncd * ncd) {
+          const int i = idx / ncd, j = idx % ncd;
+          double acc = gacc[e];
+          for (int rb = 0; rb < nt; ++rb) acc += sT2[rb * ncd + i] * sT2[rb * ncd + j];
+          gacc[e] = acc;
+        }
+      }
+      __syncthreads();
+    }
+    {
+      double *Go = G_out + (size_t)w * lay.m_stride;
+#pragma unroll
+      for (int e = 0; e < kGEPT; ++e) {
+        const int idx = tid + e * NT;
+        if (idx < ncd * ncd) Go[idx] = gacc[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_patch_select : thresholded pseudo-inverse through a cyclic Jacobi eigen-solver
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+__global__ void __launch_bounds__(512, 1)
+k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ Minv_in,
+               const double *__restrict__ G_in, double *__restrict__ cvec, double *__restrict__ diag,
+               int *__restrict__ status, SelectLayout lay) {
+  extern __shared__ double smem[];
+  const int nmax = lay.ncd_max;       // >= n + 1
+  double *sG = smem;                                   // packed lower, n(n+1)/2
+  double *sV = sG + (size_t)nmax * (nmax + 1) / 2;     // [n][n]
+  double *sg = sV + (size_t)nmax * nmax;               // g
+  double *sgh = sg + nmax;                             // V^T g
+  double *sd = sgh + nmax;                             // d
+  double *slam = sd + nmax;                            // eigenvalues
+  double *sc = slam + nmax;                            // rotation cos per pair
+  double *ss = sc + nmax;                              // rotation sin per pair
+  int *sp = (int *)(ss + nmax);                        // pair p
+  int *sq = sp + nmax;                                 // pair q
+  int *sord = sq + nmax;                               // eigenvalue order (descending |lambda|)
+  __shared__ double sRed[32];
+  __shared__ double sOff;
+  __shared__ int sFlag;
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pid = patch_ids[w];
+    const Geom g = make_geom(cP, pid);
+    const int ncd = g.Ncd, s = cP.s;
+    const double *Minv = Minv_in + (size_t)w * lay.m_stride;
+    const double *Gf = G_in + (size_t)w * lay.m_stride;
+    for (int d = 0; d < s; ++d) {
+      double *cv = cvec + ((size_t)w * s + d) * lay.ncd_max;
+      double *dg = diag + ((size_t)pid * s + d) * 8;
+      __syncthreads();
+      if (!g.slod) {  // LOD branch: c = M^{-1} e_d (source/LOD.cc:570-593)
+        for (int i = tid; i < ncd; i += NT) cv[i] = Minv[i * ncd + d];
+        if (tid == 0) { dg[0] = 0; dg[1] = 0; dg[2] = 0; dg[3] = 0; dg[5] = 0; dg[6] = 0; }
+        continue;
+      }
+      const int n = ncd - 1;               // considered_candidates
+      const int np = (n + 1) & ~1;         // even player count for the tournament
+      const int half = np / 2;
+      // other_phi: all coarse dofs but d  (source/LOD.cc:637-640)
+      for (int idx = tid; idx < n * n; idx += NT) {
+        const int i = idx / n, j = idx % n;
+        if (j <= i) sG[i * (i + 1) / 2 + j] = Gf[(i + (i >= d)) * ncd + (j + (j >= d))];
+        sV[idx] = (i == j) ? 1.0 : 0.0;
+      }
+      for (int i = tid; i < n; i += NT) sg[i] = Gf[(i + (i >= d)) * ncd + d];
+      __syncthreads();
+      double maxdiag = 0.0;
+      for (int i = 0; i < n; ++i) maxdiag = fmax(maxdiag, fabs(sG[i * (i + 1) / 2 + i]));
+      const double tol = 1e-17 * maxdiag;
+      int sweeps = 0;
+      for (; sweeps < 40; ++sweeps) {
+        if (tid == 0) sOff = 0.0;
+        __syncthreads();
+        double myoff = 0.0;
+        for (int step = 0; step < np - 1; ++step) {
+          // rotation parameters for the `half` disjoint pairs of this step
+          if (tid < half) {
+            int a, b;
+            if (tid == 0) { a = step; b = np - 1; }
+            else { a = (step + tid) % (np - 1); b = (step - tid + (np - 1)) % (np - 1); }
+            int p = min(a, b), q = max(a, b);
+            double c = 1.0, sn = 0.0;
+            if (q < n) {
+              const double apq = sG[q * (q + 1) / 2 + p];
+              myoff = fmax(myoff, fabs(apq));
+              if (fabs(apq) > tol) {
+                const double app = sG[p * (p + 1) / 2 + p], aqq = sG[q * (q + 1) / 2 + q];
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                c = 1.0 / sqrt(1.0 + t * t);
+                sn = t * c;
+              }
+            } else {
+              q = -1;  // dummy player: no rotation, but p's row still needs no update
+            }
+            sp[tid] = p; sq[tid] = q; sc[tid] = c; ss[tid] = sn;
+          }
+          __syncthreads();
+          // G <- J^T G J in 2x2 blocks (pair k1 rows, pair k2 columns), lower block triangle only
+          for (int idx = tid; idx < half * half; idx += NT) {
+            const int k1 = idx / half, k2 = idx % half;
+            if (k2 > k1) continue;
+            const int p1 = sp[k1], q1 = sq[k1], p2 = sp[k2], q2 = sq[k2];
+            const double c1 = sc[k1], s1 = ss[k1], c2 = sc[k2], s2 = ss[k2];
+            if (q1 < 0 && q2 < 0) continue;
+            if (k1 == k2) {
+              if (q1 < 0) continue;
+              const double app = sG[sym_idx(p1, p1)], aqq = sG[sym_idx(q1, q1)], apq = sG[sym_idx(q1, p1)];
+              // [c -s; s c]^T ... : new diagonal from the full similarity transform
+              const double npp = c1 * c1 * app - 2.0 * c1 * s1 * apq + s1 * s1 * aqq;
+              const double nqq = s1 * s1 * app + 2.0 * c1 * s1 * apq + c1 * c1 * aqq;
+              const double npq = (c1 * c1 - s1 * s1) * apq + c1 * s1 * (app - aqq);
+              sG[sym_idx(p1, p1)] = npp;
+              sG[sym_idx(q1, q1)] = nqq;
+              sG[sym_idx(q1, p1)] = (s1 != 0.0) ? 0.0 : npq;
+              continue;
+            }
+            // rows {p1,q1} (q1 may be absent), cols {p2,q2} (q2 may be absent)
+            double b00 = sG[sym_idx(p1, p2)];
+            double b01 = (q2 >= 0) ? sG[sym_idx(p1, q2)] : 0.0;
+            double b10 = (q1 >= 0) ? sG[sym_idx(q1, p2)] : 0.0;
+            double b11 = (q1 >= 0 && q2 >= 0) ? sG[sym_idx(q1, q2)] : 0.0;
+            const double t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
+            const double t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
+            b00 = c2 * t00 - s2 * t01; b01 = s2 * t00 + c2 * t01;
+            b10 = c2 * t10 - s2 * t11; b11 = s2 * t10 + c2 * t11;
+            sG[sym_idx(p1, p2)] = b00;
+            if (q2 >= 0) sG[sym_idx(p1, q2)] = b01;
+            if (q1 >= 0) sG[sym_idx(q1, p2)] = b10;
+            if (q1 >= 0 && q2 >= 0) sG[sym_idx(q1, q2)] = b11;
+          }
+          // V <- V J
+          for (int idx = tid; idx < n * half; idx += NT) {
+            const int r = idx / half, k = idx % half;
+            const int q = sq[k];
+            if (q < 0) continue;
+            const int p = sp[k];
+            const double c = sc[k], sn = ss[k];
+            const double vp = sV[r * n + p], vq = sV[r * n + q];
+            sV[r * n + p] = c * vp - sn * vq;
+            sV[r * n + q] = sn * vp + c * vq;
+          }
+          __syncthreads();
+        }
+        // converged when no off-diagonal entry seen in this sweep exceeded tol
+        myoff = warp_max(myoff);
+        if (lane == 0) sRed[warp] = myoff;
+        __syncthreads();
+        if (tid == 0) {
+          double m = 0.0;
+          for (int i = 0; i < nwarp; ++i) m = fmax(m, sRed[i]);
+          sOff = m;
+        }
+        __syncthreads();
+        if (sOff <= tol) { ++sweeps; break; }
+      }
+      // eigenvalues, order by descending |lambda| (LAPACK singular value order), ghat = V^T g
+      for (int i = tid; i < n; i += NT) slam[i] = sG[i * (i + 1) / 2 + i];
+      __syncthreads();
+      for (int i = tid; i < n; i += NT) {
+        const double li = fabs(slam[i]);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const double lj = fabs(slam[j]);
+          rank += (lj > li) || (lj == li && j < i);
+        }
+        sord[rank] = i;
+        double acc = 0.0;
+        for (int r = 0; r < n; ++r) acc += sV[r * n + i] * sg[r];
+        sgh[i] = acc;
+      }
+      __syncthreads();
+      const double sig0 = fabs(slam[sord[0]]);
+      // d = - sum_k v_k w_k ghat_k, w_k = 1/lambda_k if |lambda_k| > 1e-15 sigma_0 (source/LOD.cc:667-671)
+      for (int r = tid; r < n; r += NT) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double lk = slam[k];
+          if (fabs(lk) > 1e-15 * sig0) acc += sV[r * n + k] * (sgh[k] / lk);
+        }
+        sd[r] = -acc;
+      }
+      __syncthreads();
+      // truncation loop (source/LOD.cc:703-725), one warp
+      if (warp == 0) {
+        int steps = 0;
+        double dinf0 = -1.0, kept = fabs(slam[sord[n - 1]]);
+        int i = n - 1;
+        for (; i >= 0; --i) {
+          double m = 0.0;
+          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sd[r]));
+          m = warp_max(m);
+          if (dinf0 < 0.0) dinf0 = m;
+          if (m < 0.5) break;
+          const int k = sord[i];
+          const double lk = slam[k];
+          if (fabs(lk) > 1e-15 * sig0) {
+            const double f = sgh[k] / lk;
+            for (int r = lane; r < n; r += 32) sd[r] += sV[r * n + k] * f;
+          }
+          __syncwarp();
+          ++steps;
+        }
+        // smallest singular value still in use
+        {
+          int last = n - 1 - steps;
+          if (last < 0) last = 0;
+          while (last > 0 && !(fabs(slam[sord[last]]) > 1e-15 * sig0)) --last;
+          kept = fabs(slam[sord[last]]);
+        }
+        if (lane == 0) {
+          dg[0] = dinf0; dg[1] = steps; dg[2] = sig0; dg[3] = kept; dg[5] = 2; dg[6] = sweeps;
+          if (sweeps >= 40) atomicOr(&status[pid], 4);
+        }
+      }
+      __syncthreads();
+      // c = M^{-1} (e_d + sum_k d_k e_other[k])  (source/LOD.cc:727-743)
+      for (int i = tid; i < ncd; i += NT) {
+        double acc = Minv[i * ncd + d];
+        for (int k = 0; k < n; ++k) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
+        cv[i] = acc;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_patch_finish : phi = X c (zero on every boundary dof), normalise, A phi
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
+               const double *__restrict__ Xbuf, const double *__restrict__ cvec, double *__restrict__ phi_out,
+               double *__restrict__ aphi_out, FinishLayout lay) {
+  extern __shared__ double smem[];
+  double *sCoef = smem;
+  double *sPhi = sCoef + lay.coef_doubles;  // [Nf]
+  double *sC = sPhi + lay.nf_max;           // [ncd]
+  __shared__ double sRed[32];
+  __shared__ double sNorm;
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pid = patch_ids[w];
+    const Geom g = make_geom(cP, pid);
+    const int ncd = g.Ncd, s = cP.s;
+    const double *X = Xbuf + (size_t)w * lay.x_stride;
+    __syncthreads();
+    load_coef(g, d_coef, sCoef);
+    for (int d = 0; d < s; ++d) {
+      __syncthreads();
+      for (int i = tid; i < ncd; i += NT) sC[i] = cvec[((size_t)w * s + d) * lay.ncd_max + i];
+      for (int i = tid; i < g.Nf; i += NT) sPhi[i] = 0.0;
+      __syncthreads();
+      double nrm = 0.0;
+      for (int r = warp; r < g.Ni; r += nwarp) {
+        double acc = 0.0;
+        for (int col = lane; col < ncd; col += 32) acc += X[(size_t)r * lay.ldx + col] * sC[col];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          int a[3], ca;
+          idof_to_node(g, r, a, ca);
+          sPhi[node_index(g, a) * s + ca] = acc;
+          nrm += acc * acc;
+        }
+      }
+      if (lane == 0) sRed[warp] = nrm;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nwarp; ++i) t += sRed[i];
+        sNorm = sqrt(t);
+      }
+      __syncthreads();
+      const double inv = 1.0 / sNorm;
+      for (int i = tid; i < g.Nf; i += NT) sPhi[i] *= inv;
+      __syncthreads();
+      double *po = phi_out + ((size_t)pid * s + d) * lay.nf_max;
+      double *ao = aphi_out + ((size_t)pid * s + d) * lay.nf_max;
+      for (int i = tid; i < lay.nf_max; i += NT) {
+        double v = 0.0, av = 0.0;
+        if (i < g.Nf) {
+          v = sPhi[i];
+          int a[3];
+          node_coords(g, i / s, a);
+          const int ca = i % s;
+          if (node_class(cP, g, a) & 2) {
+            av = v;  // domain-boundary rows of semi_constrained are identity rows (source/LOD.cc:537-541)
+          } else {
+            const int nst = (cP.dim == 3) ? 27 : 9;
+            for (int e = 0; e < nst; ++e) {
+              int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
+              int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
+              bool ok = true;
+              for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 0 && b[x] <= g.p[x] - 1);
+              if (!ok) continue;
+              const int nb_ = node_index(g, b);
+              for (int cb = 0; cb < s; ++cb) {
+                const double pv = sPhi[nb_ * s + cb];
+                if (pv != 0.0) av += stiff_entry(cP, g, sCoef, a, dl, ca, cb) * pv;
+              }
+            }
+          }
+        }
+        po[i] = v;
+        ao[i] = av;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_coarse : K rows of one patch in block-ELL form
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const double *__restrict__ aphi,
+         double *__restrict__ Kell, FinishLayout lay) {
+  extern __shared__ double smem[];
+  double *sPhi = smem;  // [s][Nf]
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int s = cP.s, n = cP.n, w = cP.w, ww = 2 * w + 1;
+  const int nslots = (cP.dim == 3) ? ww * ww * ww : ww * ww;
+  for (int pid = patch_begin + blockIdx.x; pid < patch_end; pid += gridDim.x) {
+    const Geom g = make_geom(cP, pid);
+    __syncthreads();
+    for (int i = tid; i < s * lay.nf_max; i += NT) sPhi[i] = phi[(size_t)pid * s * lay.nf_max + i];
+    __syncthreads();
+    int cen[3] = {g.lo[0] + g.cc[0], g.lo[1] + g.cc[1], g.lo[2] + g.cc[2]};
+    for (int item = warp; item < nslots * s * s; item += nwarp) {
+      const int e = item % s, d = (item / s) % s, slot = item / (s * s);
+      int D[3] = {slot % ww - w, (slot / ww) % ww - w, (cP.dim == 3) ? slot / (ww * ww) - w : 0};
+      int qc[3] = {cen[0] + D[0], cen[1] + D[1], cen[2] + D[2]};
+      double val = 0.0;
+      bool valid = true;
+      for (int x = 0; x < cP.dim; ++x) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
+      if (valid) {
+        const int qid = (int)morton_encode(qc, cP.dim, cP.ref);
+        const Geom gq = make_geom(cP, qid);
+        // overlap box in global node coordinates
+        int b0[3], b1[3], cnt = 1;
+        for (int x = 0; x < 3; ++x) {
+          if (x < cP.dim) {
+            b0[x] = max(g.lo[x], gq.lo[x]) * n;
+            b1[x] = min(g.lo[x] + g.m[x], gq.lo[x] + gq.m[x]) * n;
+            if (b1[x] < b0[x]) valid = false;
+          } else {
+            b0[x] = 0; b1[x] = 0;
+          }
+          cnt *= (b1[x] - b0[x] + 1);
+        }
+        if (valid) {
+          const double *aq = aphi + ((size_t)qid * s + e) * lay.nf_max;
+          const double *pp = sPhi + d * lay.nf_max;
+          const int ex = b1[0] - b0[0] + 1, ey = b1[1] - b0[1] + 1;
+          double acc = 0.0;
+          for (int t = lane; t < cnt; t += 32) {
+            const int ix = t % ex, iy = (t / ex) % ey, iz = t / (ex * ey);
+            const int gx = b0[0] + ix, gy = b0[1] + iy, gz = b0[2] + iz;
+            const int np_ = ((gz - g.lo[2] * n) * g.p[1] + (gy - g.lo[1] * n)) * g.p[0] + (gx - g.lo[0] * n);
+            const int nq_ = ((gz - gq.lo[2] * n) * gq.p[1] + (gy - gq.lo[1] * n)) * gq.p[0] + (gx - gq.lo[0] * n);
+            for (int c = 0; c < s; ++c) acc += pp[np_ * s + c] * aq[nq_ * s + c];
+          }
+          val = warp_sum(acc);
+        }
+      }
+      if (lane == 0) Kell[((size_t)pid * s + d) * cP.ell_width + slot * s + e] = val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                               double *X, double *Lws, int *status, const SolveLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_solve<kSolveNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_solve<kSolveNB><<<grid, lay.threads, smem, st>>>(ids, n_work, coef, X, Lws, status, lay);
+  return cudaGetLastError();
+}
+cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                               const double *X, double *Minv, double *G, double *diag, int *status,
+                               const DenseLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_dense<<<grid, lay.threads, smem, st>>>(ids, n_work, coef, X, Minv, G, diag, status, lay);
+  return cudaGetLastError();
+}
+cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
+                                const double *G, double *cvec, double *diag, int *status, const SelectLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_select<<<grid, lay.threads, smem, st>>>(ids, n_work, Minv, G, cvec, diag, status, lay);
+  return cudaGetLastError();
+}
+cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                                const double *X, const double *cvec, double *phi, double *aphi,
+                                const FinishLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_finish<<<grid, 256, smem, st>>>(ids, n_work, coef, X, cvec, phi, aphi, lay);
+  return cudaGetLastError();
+}
+cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
+                          double *Kell, const FinishLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_coarse<<<grid, 256, smem, st>>>(p0, p1, phi, aphi, Kell, lay);
+  return cudaGetLastError();
+}
+
+}  // namespace slod

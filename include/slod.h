@@ -1,0 +1,148 @@
+/*
+ * slod.h -- C ABI of the B200-native SLOD offline phase (libslod_b200.so).
+ *
+ * The reference (camillabelponer/dealii-slod) has no FFI layer: the seam this library replaces is
+ * the pair of protected member functions
+ *     LOD::compute_basis_function_candidates()   source/LOD.cc:296-768   (declared include/LOD.h:176)
+ *     LOD::assemble_global_matrix()              source/LOD.cc:860-973   (declared include/LOD.h:178)
+ * called from LOD::run() (source/LOD.cc:1433-1434), together with the integer set-up they depend on
+ * (create_patches source/LOD.cc:122-244, create_mesh_for_patch :770-858, fill_dofs_indices_vector
+ * include/LODtools.h:334-375) and the PDE hook assemble_stiffness (include/Diffusion.h:111-207,
+ * include/Elasticity.h:163-299).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *  - plain C, opaque handle, no exceptions cross the boundary; every call returns an int status
+ *    (SLOD_OK == 0) and slod_last_error() gives the message of the last failure on that handle.
+ *  - all floating point data is fp64; all buffers are caller-owned.
+ *  - one handle drives ONE CUDA device (one process per GPU; the collective between ranks is done
+ *    by the caller on the device buffers, see slod_*_device entry points).
+ *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
+ *  - patch id == active-cell index of the centre cell after refine_global (Morton / Z-order, x low
+ *    bit), exactly as in source/LOD.cc:184-192.
+ *  - patch-local fine nodes are numbered lexicographically (x fastest) on the patch's own node box
+ *    (p_a = m_a * n_subdivisions + 1 nodes along axis a); a fine DoF is spacedim*node + comp.
+ *    slod_get_patch_fine_dofs() maps them to deal.II's global fine DoF numbers,
+ *    slod_get_patch_local_dofs() to deal.II's patch-local numbers (Patch::basis_function layout,
+ *    include/LOD.h:79).
+ */
+#ifndef SLOD_B200_H
+#define SLOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slod_ctx slod_ctx;
+
+enum {
+  SLOD_OK = 0,
+  SLOD_ERR_INVALID = 1,      /* bad argument / inconsistent parameters                  */
+  SLOD_ERR_UNSUPPORTED = 2,  /* configuration outside the implemented envelope           */
+  SLOD_ERR_CUDA = 3,         /* CUDA runtime error or no usable device                   */
+  SLOD_ERR_STATE = 4,        /* call order violated (e.g. basis requested before compute) */
+  SLOD_ERR_NUMERIC = 5       /* a patch problem was not SPD / eigen-solver did not converge */
+};
+
+enum { SLOD_PROBLEM_DIFFUSION = 0, SLOD_PROBLEM_ELASTICITY = 1 };
+/* slod_params.device: -1 = current CUDA device; SLOD_DEVICE_NONE = no device, integer maps only
+ * (patch lists, DoF maps, CSR pattern) -- every compute call on such a handle returns SLOD_ERR_CUDA. */
+enum { SLOD_DEVICE_CURRENT = -1, SLOD_DEVICE_NONE = -2 };
+
+/* Mirrors LODParameters (include/LOD.h:85-157) + the template arguments <dim, spacedim>. */
+typedef struct {
+  int dim;                  /* 2 or 3 (3 only with spacedim 1)                                   */
+  int spacedim;             /* 1 diffusion, 2 = dim elasticity                                    */
+  int n_global_refinements; /* "Number of global refinements"                 include/LOD.h:95   */
+  int n_subdivisions;       /* "Number of subdivisions" (power of two)        include/LOD.h:94   */
+  int oversampling;         /* "Oversampling"                                 include/LOD.h:93   */
+  int stabilize;            /* "Stabilize phi_LOD candidates" (SLOD)          include/LOD.h:97   */
+  int problem;              /* SLOD_PROBLEM_*                                                     */
+  int quirk_presaved;       /* reproduce source/LOD.cc:354-362 ("Constant problem coefficients") */
+  int device;               /* CUDA device ordinal, SLOD_DEVICE_CURRENT or SLOD_DEVICE_NONE        */
+} slod_params;
+
+/* life cycle ------------------------------------------------------------------------------------*/
+int slod_create(const slod_params *par, slod_ctx **out);
+void slod_destroy(slod_ctx *ctx);
+const char *slod_last_error(const slod_ctx *ctx);
+/* message of the last failed slod_create (which has no handle to ask) */
+const char *slod_last_create_error(void);
+
+/* coefficients: replaces problem_parameter (include/Diffusion.h:7-54).  `cellwise` holds one value
+ * per cell of a (2^eta_refinement)^dim grid, lexicographic x fastest.  field 0 = alpha | lambda,
+ * field 1 = mu.  Requires 2^eta_refinement <= 2^n_global_refinements * n_subdivisions (the table is
+ * then constant on every fine sub-cell, as in all reference configurations). */
+int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const double *cellwise, size_t n);
+
+/* integer maps (bit-exact with the reference / the oracle) -----------------------------------------*/
+int slod_patch_count(const slod_ctx *ctx, int64_t *n_patches);
+/* sizes of one patch: cells, fine DoFs, interior DoFs, patch-boundary DoFs (id 99), domain-boundary
+ * DoFs (id 0), coarse DoFs; and the node box m[a] cells / lo[a] first coarse cell per axis. */
+int slod_get_patch_info(const slod_ctx *ctx, int64_t patch, int32_t *n_cells, int32_t *n_fine, int32_t *n_internal,
+                        int32_t *n_boundary, int32_t *n_domain_boundary, int32_t *n_coarse, int32_t lo[3],
+                        int32_t m[3]);
+/* Patch::cells (active-cell ids, centre first, x-offset outer)            source/LOD.cc:151-201 */
+int slod_get_patch_cells(const slod_ctx *ctx, int64_t patch, uint32_t *cells, int32_t *n);
+/* lexicographic patch DoF -> deal.II global fine DoF (dof_handler_fine)    source/LOD.cc:925-929 */
+int slod_get_patch_fine_dofs(const slod_ctx *ctx, int64_t patch, uint64_t *global_dofs, int32_t *n);
+/* lexicographic patch DoF -> deal.II patch-local DoF (dh_fine_patch)       source/LOD.cc:365-366 */
+int slod_get_patch_local_dofs(const slod_ctx *ctx, int64_t patch, uint32_t *local_dofs, int32_t *n);
+/* fill_dofs_indices_vector (lexicographic patch numbering, ascending)  include/LODtools.h:334-375
+ * which: 0 internal, 1 patch boundary (id 99), 2 domain boundary (id 0). */
+int slod_get_patch_dof_class(const slod_ctx *ctx, int64_t patch, int which, uint32_t *dofs, int32_t *n);
+
+/* the hot path, host buffers ------------------------------------------------------------------------*/
+/* stages assembly .. premultiply for every patch (source/LOD.cc:345-767), batched on the GPU. */
+int slod_compute_basis(slod_ctx *ctx);
+/* Patch::basis_function[comp] and basis_function_premultiplied[comp] (include/LOD.h:79-80) in
+ * lexicographic patch numbering; either pointer may be NULL. n_fine values each. */
+int slod_get_basis(const slod_ctx *ctx, int64_t patch, int comp, double *phi, double *A_phi);
+/* all patches at once: arrays [n_patches][spacedim][stride] with stride = slod_basis_stride(). */
+int slod_basis_stride(const slod_ctx *ctx, int64_t *stride);
+int slod_get_all_basis(const slod_ctx *ctx, double *phi, double *A_phi);
+/* global_stiffness_matrix = C^T (A C)  (source/LOD.cc:860-973). */
+int slod_assemble_coarse(slod_ctx *ctx);
+/* CSR of the coarse matrix (rows/cols = spacedim*patch + comp, columns ascending; structural zeros of
+ * the sparse product are kept).  Call with rowptr == NULL to query n_rows and nnz. */
+int slod_get_coarse_csr(const slod_ctx *ctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
+                        int64_t *nnz);
+
+/* diagnostics: per patch and component 8 doubles:
+ *   [0] ||d||_inf before truncation  [1] truncation steps  [2] sigma_0  [3] smallest kept sigma
+ *   [4] cond(M) estimate (max/min Cholesky pivot squared) [5] selection path (0 LOD, 1 Cholesky, 2 eigen)
+ *   [6] Jacobi sweeps [7] status bits */
+int slod_get_patch_diagnostics(const slod_ctx *ctx, int64_t patch, int comp, double out[8]);
+/* stage intermediates of one patch for staged parity tests (recomputed on demand for that patch):
+ * X = A_ii^{-1} P_i  (n_internal x n_coarse, row-major), Minv (n_coarse^2), BD^T BD (n_coarse^2). Any may be NULL. */
+int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Minv, double *G);
+
+/* per-kernel device times of the last compute/assemble (CUDA events), ms:
+ *   [0] patch solve  [1] dense (M, BD, Gram)  [2] selection (eigen)  [3] finish (phi, A phi)
+ *   [4] coarse matrix  [5] H2D  [6] D2H  [7] total device */
+int slod_get_timings(const slod_ctx *ctx, double *ms, int n);
+
+/* the hot path, device buffers (multi-GPU plumbing) ----------------------------------------------------*/
+/* Compute the basis of patches [patch_begin, patch_end) into device arrays laid out
+ * [n_patches][spacedim][stride]; only the rows of the range are written.  `stream` is a cudaStream_t. */
+int slod_compute_basis_device(slod_ctx *ctx, int64_t patch_begin, int64_t patch_end, double *d_phi, double *d_A_phi,
+                              void *stream);
+/* Coarse-matrix rows of patches [patch_begin, patch_end) in block-ELL form: d_K is
+ * [n_patches*spacedim][ell_width] with ell_width = (4*oversampling+3)^dim * spacedim; slot of neighbour
+ * offset D and component e is ((Dz+w)*(2w+1)+(Dy+w))*(2w+1)+(Dx+w))*spacedim+e, w = 2*oversampling+1.
+ * Needs d_phi of the range and d_A_phi of ALL patches (all-gathered by the caller). */
+int slod_assemble_coarse_device(slod_ctx *ctx, int64_t patch_begin, int64_t patch_end, const double *d_phi,
+                                const double *d_A_phi, double *d_K, void *stream);
+int slod_ell_width(const slod_ctx *ctx, int64_t *width);
+/* convert a host copy of the block-ELL matrix into CSR (same contract as slod_get_coarse_csr) */
+int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,
+                    int64_t *n_rows, int64_t *nnz);
+/* number of kernels launched by this handle so far */
+int slod_launch_count(const slod_ctx *ctx, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOD_B200_H */

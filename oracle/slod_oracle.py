@@ -552,6 +552,10 @@ class SlodOracle:
             info["trunc_steps"] = []
             info["cond_G"] = []
             info["dinf"] = []
+            info["sigma"] = []
+            info["G"] = BD.T @ BD
+            info["Minv"] = Minv
+            info["X"] = Xi
             for d in range(s):
                 B_d0 = BD[:, d]
                 other = [k for k in range(shape.Ncd) if k != d]     # :637-640
@@ -563,6 +567,7 @@ class SlodOracle:
                 d_i = -(Vt.T @ (winv * (U.T @ g)))        # :669-671
                 info["cond_G"].append(float(sig[0] / sig[-1]) if sig[-1] > 0 else float("inf"))
                 info["dinf"].append(float(np.abs(d_i).max()))
+                info["sigma"].append(sig.copy())
                 steps = 0
                 for i in range(ncand - 1, -1, -1):        # :703-725
                     if np.abs(d_i).max() < 0.5:

@@ -1,0 +1,131 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (fp64): every stage up to the Gram matrix is compared at 1e-10 relative; the selected basis at
+1e-10 where the reference's own selection is well conditioned and at c*eps*cond_eff elsewhere, because the
+reference solves the selection through the Gram matrix with a thresholded SVD (source/LOD.cc:656-725) and two
+correct fp64 implementations differ by that much; integer maps bit-exact."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+from parity_common import (EPS, build_pair, cond_eff, margin_safe, patch_tolerance, pkg)  # noqa: E402
+from oracle.slod_oracle import GlibcRand, reference_random_table  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _global_lex_nodes(info, n, G):
+    lo, m = info["lo"], info["m"]
+    dim = len(lo)
+    p = [mm * n + 1 for mm in m]
+    idx = np.indices(p[::-1]).reshape(dim, -1)[::-1]  # x fastest
+    g = np.zeros(idx.shape[1], dtype=np.int64)
+    mul = 1
+    for a in range(dim):
+        g += (idx[a] + lo[a] * n) * mul
+        mul *= G
+    return g
+
+
+def test_poisson_lod_example_golden(golden_dir):
+    """tests/Poisson_LOD_Example.output through the CUDA path: rhs l2 norm = 0.0808367."""
+    txt = open(os.path.join(golden_dir, "Poisson_LOD_Example.output")).read()
+    rhs_norm = float(re.search(r"\n\s+rhs l2 norm = ([0-9.]+)", txt).group(1))
+    rng = GlibcRand()
+    for _ in range(12):
+        rng.rand()
+    tab = reference_random_table(2, 1, 100, 8, rng)
+    ctx, orc = build_pair(dim=2, s=1, ref=2, n=2, ell=1, stabilize=False, r=8, quirk=True, tables=[tab])
+    ctx.compute_basis()
+    orc.compute_basis()
+    f = orc.fem_rhs_constant_one()
+    rhs = np.zeros(ctx.n_patches)
+    for res in orc.patches:
+        phi, aphi = ctx.basis(res.pid)
+        assert np.linalg.norm(phi - res.basis[0]) < 1e-10
+        assert np.linalg.norm(aphi - res.basis_premultiplied[0]) < 1e-10 * np.linalg.norm(res.basis_premultiplied[0])
+        rhs[res.pid] = phi @ f[_global_lex_nodes(ctx.patch_info(res.pid), 2, 9)]
+    assert float("%g" % np.linalg.norm(rhs)) == rhs_norm
+
+
+CASES = [
+    dict(dim=2, s=1, ref=3, n=2, ell=1, stabilize=False),            # LOD branch
+    dict(dim=2, s=1, ref=4, n=2, ell=1),                             # SLOD, small patches
+    dict(dim=2, s=1, ref=4, n=2, ell=2),                             # cfg 2 shape
+    dict(dim=2, s=1, ref=2, n=2, ell=3),                             # every patch is the whole domain -> LOD
+    dict(dim=2, s=1, ref=3, n=4, ell=1),                             # 4 subdivisions
+    dict(dim=2, s=2, ref=3, n=2, ell=1),                             # cfg 3 shape (elasticity)
+    dict(dim=2, s=2, ref=4, n=2, ell=2, sample=40),
+    dict(dim=2, s=1, ref=4, n=2, ell=2, kind="binary1e4", seed=1235),  # high contrast
+    dict(dim=3, s=1, ref=2, n=2, ell=1),
+    dict(dim=3, s=1, ref=3, n=2, ell=2, sample=10, kind="uniform1e4", seed=3001),   # cfg 4 shape
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_basis_and_coarse_matrix(case):
+    case = dict(case)
+    sample = case.pop("sample", None)
+    ctx, orc = build_pair(**case)
+    s = case["s"]
+    ctx.compute_basis()
+    ctx.assemble_coarse()
+    npch = ctx.n_patches
+    pids = list(range(npch)) if sample is None else sorted(set(range(0, npch, max(1, npch // sample))) | {npch - 1})
+    orc.compute_basis(pids)
+    tol_of = {}
+    n_checked_tight = 0
+    for res in orc.patches:
+        for d in range(s):
+            phi, aphi = ctx.basis(res.pid, d)
+            dg = ctx.diagnostics(res.pid, d)
+            assert dg[7] == 0
+            if not margin_safe(res.info, d):
+                tol_of[(res.pid, d)] = None     # decision within rounding of flipping: not comparable
+                continue
+            tol = patch_tolerance(res.info, d)
+            tol_of[(res.pid, d)] = tol
+            n_checked_tight += tol == 1e-10
+            if res.info["slod"]:
+                assert int(dg[1]) == res.info["trunc_steps"][d], (res.pid, d)
+            assert np.linalg.norm(phi - res.basis[d]) <= tol, (res.pid, d, cond_eff(res.info, d) if res.info["slod"] else 1)
+            nrm = np.linalg.norm(res.basis_premultiplied[d])
+            assert np.linalg.norm(aphi - res.basis_premultiplied[d]) <= 10 * tol * nrm, (res.pid, d)
+    assert n_checked_tight > 0
+    # stages up to the Gram matrix on a few SLOD patches: 1e-10 relative, no conditioning excuse
+    for res in [r for r in orc.patches if r.info["slod"]][:: max(1, len(orc.patches) // 5)]:
+        X, Minv, G = ctx.debug_stages(res.pid)
+        for got, want in ((X, res.info["X"]), (Minv, res.info["Minv"]), (G, res.info["G"])):
+            assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max(), res.pid
+    if sample is None:
+        K, _, _ = orc.assemble_global_matrix()
+        rowptr, col, val = ctx.coarse_csr()
+        assert np.array_equal(rowptr, K.indptr) and np.array_equal(col, K.indices)      # bit-exact pattern
+        kmax = np.abs(K.data).max()
+        rows = np.repeat(np.arange(K.shape[0]), np.diff(K.indptr))
+        tol_row = np.array([tol_of.get((r // s, r % s)) or np.inf for r in range(K.shape[0])])
+        tol_e = 20 * (tol_row[rows] + tol_row[col])
+        assert (np.abs(val - K.data) <= tol_e * kmax).all()
+        tight = np.isfinite(tol_e) & (tol_e <= 20 * 2e-10)
+        assert tight.any()
+        assert np.abs(val - K.data)[tight].max() <= 4e-9 * kmax
+
+
+def test_linearity_in_coefficient_scaling():
+    """Size-independent property: scaling alpha by c leaves phi unchanged and scales A phi and K by c."""
+    ctx1, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, kind="uniform100", seed=5)
+    tabs = [4.0 * t for t in __import__("parity_common").make_tables(2, 1, 5, "uniform100", 5)]
+    ctx2, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, tables=tabs, r=5)
+    for c in (ctx1, ctx2):
+        c.compute_basis()
+        c.assemble_coarse()
+    p1, a1 = ctx1.all_basis()
+    p2, a2 = ctx2.all_basis()
+    for pid in range(ctx1.n_patches):
+        if ctx1.diagnostics(pid)[1] == 0 and ctx1.diagnostics(pid)[0] < 0.45:
+            assert np.abs(p1[pid] - p2[pid]).max() < 1e-9
+            assert np.abs(4.0 * a1[pid] - a2[pid]).max() < 1e-9 * np.abs(a2[pid]).max()
