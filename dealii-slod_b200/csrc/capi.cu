@@ -36,6 +36,9 @@ struct slod_ctx {
   int64_t n_patches = 0;
   int n_fields = 1;
   bool coef_set[2] = {false, false};
+  std::vector<double> coef_table[2];  // caller's cell-wise tables
+  int coef_r[2] = {0, 0};
+  bool coef_dirty = true;
   double *d_coef = nullptr;  // [n_fields][nsub^dim]
   size_t coef_field_elems = 0;
   // results owned by the handle (host-buffer API)
@@ -96,6 +99,8 @@ void reference_matrices(Params &P) {
   const double jxw = std::pow(h / 2.0, dim);
   std::fill(P.Kref, P.Kref + kMaxLocal * kMaxLocal, 0.0);
   std::fill(P.Klam, P.Klam + kMaxLocal * kMaxLocal, 0.0);
+  std::memset(P.Kq, 0, sizeof(P.Kq));
+  std::memset(P.Klamq, 0, sizeof(P.Klamq));
   for (int q = 0; q < nn; ++q) {
     double x[3] = {pts[q & 1], pts[(q >> 1) & 1], pts[(q >> 2) & 1]};
     double G[8][3];
@@ -116,6 +121,7 @@ void reference_matrices(Params &P) {
           double d = 0;
           for (int a = 0; a < dim; ++a) d += G[i][a] * G[j][a];
           P.Kref[i * nl + j] += d * jxw;
+          P.Kq[q][i * nl + j] = d * jxw;
         }
     } else {
       // 2 eps(phi_i):eps(phi_j) and div phi_i div phi_j   (include/Elasticity.h:236-250)
@@ -132,6 +138,8 @@ void reference_matrices(Params &P) {
                 }
               P.Kref[(i * s + ci) * nl + (j * s + cj)] += 2.0 * ee * jxw;
               P.Klam[(i * s + ci) * nl + (j * s + cj)] += G[i][ci] * G[j][cj] * jxw;
+              P.Kq[q][(i * s + ci) * nl + (j * s + cj)] = 2.0 * ee * jxw;
+              P.Klamq[q][(i * s + ci) * nl + (j * s + cj)] = G[i][ci] * G[j][cj] * jxw;
             }
     }
   }
@@ -221,6 +229,54 @@ void free_dev(slod_ctx *c) {
   F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
 }
 
+// Expand the caller's tables (problem_parameter::value, include/Diffusion.h:40-53) onto the fine sub-cell
+// grid: one value per sub-cell when eta >= h, one per Gauss point of the 2-point rule when eta < h.
+int prepare_coefficients(slod_ctx *ctx) {
+  Params &P = ctx->P;
+  if (!ctx->coef_dirty) return SLOD_OK;
+  int gauss = 0;
+  for (int f = 0; f < ctx->n_fields; ++f) {
+    if (!ctx->coef_set[f]) return fail(ctx, SLOD_ERR_STATE, "coefficient field not set");
+    if ((1 << ctx->coef_r[f]) > P.nsub) gauss = 1;
+  }
+  const int nq = gauss ? (1 << P.dim) : 1;
+  const int mfull = std::min(2 * P.ell + 1, P.N);
+  const size_t need = (size_t)ctx->n_fields * ipow(P.n * mfull, P.dim) * nq;
+  if ((int)need > ctx->sl.coef_doubles)
+    return fail(ctx, SLOD_ERR_UNSUPPORTED,
+                "coefficient finer than the fine sub-cells (eta < h) needs per-Gauss-point storage that does not "
+                "fit the shared-memory plan of this configuration");
+  const int ns = P.nsub, nz = (P.dim == 3) ? ns : 1;
+  const size_t per_field = (size_t)ns * ns * nz * nq;
+  std::vector<double> fine(per_field * ctx->n_fields);
+  const double gp[2] = {0.5 - 0.5 / std::sqrt(3.0), 0.5 + 0.5 / std::sqrt(3.0)};
+  for (int f = 0; f < ctx->n_fields; ++f) {
+    const int nl = 1 << ctx->coef_r[f];
+    const std::vector<double> &tab = ctx->coef_table[f];
+    double *out = fine.data() + (size_t)f * per_field;
+    auto lookup = [&](int sub, int qbit) -> int {
+      if (nl <= ns) return sub / (ns / nl);
+      // floor(x / eta) with x = (sub + gp) h and eta = h / ratio
+      const int ratio = nl / ns;
+      return sub * ratio + (int)std::floor(gp[qbit] * ratio);
+    };
+    for (int z = 0; z < nz; ++z)
+      for (int y = 0; y < ns; ++y)
+        for (int x = 0; x < ns; ++x)
+          for (int q = 0; q < nq; ++q) {
+            const int ix = lookup(x, q & 1), iy = lookup(y, (q >> 1) & 1), iz = (P.dim == 3) ? lookup(z, (q >> 2) & 1) : 0;
+            out[(((size_t)z * ns + y) * ns + x) * nq + q] = tab[((size_t)iz * nl + iy) * nl + ix];
+          }
+  }
+  if (ctx->d_coef) cudaFree(ctx->d_coef);
+  ctx->d_coef = nullptr;
+  CK(cudaMalloc(&ctx->d_coef, sizeof(double) * fine.size()));
+  CK(cudaMemcpy(ctx->d_coef, fine.data(), sizeof(double) * fine.size(), cudaMemcpyHostToDevice));
+  P.gauss_coef = gauss;
+  ctx->coef_dirty = false;
+  return SLOD_OK;
+}
+
 int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   const Params &P = ctx->P;
   if (ctx->chunk > 0) return SLOD_OK;
@@ -243,11 +299,11 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
 
 int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_aphi, cudaStream_t st) {
   const Params &P = ctx->P;
-  for (int f = 0; f < ctx->n_fields; ++f)
-    if (!ctx->coef_set[f]) return fail(ctx, SLOD_ERR_STATE, "coefficient field not set");
   if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
   if (p0 == p1) return SLOD_OK;
-  int rc = ensure_workspace(ctx, p1 - p0);
+  int rc = prepare_coefficients(ctx);
+  if (rc) return rc;
+  rc = ensure_workspace(ctx, p1 - p0);
   if (rc) return rc;
   CK(upload_params(P));
   // work order: largest patches first
@@ -457,6 +513,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   P.Hd = std::pow(P.H, P.dim);
   P.pw = std::pow(P.h, P.dim) / (double)(1 << P.dim);
   P.has_presaved = 0;
+  P.gauss_coef = 0;
   ctx->n_patches = (int64_t)ipow(P.N, P.dim);
   ctx->n_fields = (P.problem == SLOD_PROBLEM_DIFFUSION) ? 1 : 2;
   reference_matrices(P);
@@ -495,7 +552,8 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   ctx->nb_max = nb_max;
   const bool big = (P.dim == 3);
   const int msub = P.n * mfull;
-  const int coef_doubles = ctx->n_fields * ipow(msub, P.dim);
+  // room for one value per Gauss point (eta < h) where that is cheap (2-D); 3-D keeps one per sub-cell
+  const int coef_doubles = ctx->n_fields * ipow(msub, P.dim) * (P.dim == 2 ? 4 : 1);
   // ---- layouts ----
   SolveLayout &sl = ctx->sl;
   sl.threads = big ? 512 : 128;
@@ -558,8 +616,6 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     *out = ctx;
     return SLOD_OK;
   }
-  if ((e = cudaMalloc(&ctx->d_coef, sizeof(double) * ctx->coef_field_elems * ctx->n_fields)) != cudaSuccess)
-    return cuda_bad("cudaMalloc coef", e);
   if ((e = cudaMalloc(&ctx->d_status, sizeof(int) * ctx->n_patches)) != cudaSuccess) return cuda_bad("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->d_diag, sizeof(double) * 8 * P.s * ctx->n_patches)) != cudaSuccess)
     return cuda_bad("cudaMalloc", e);
@@ -592,21 +648,10 @@ int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const dou
   if (eta_refinement < 0 || eta_refinement > 15) return fail(ctx, SLOD_ERR_INVALID, "eta_refinement out of range");
   const int nl = 1 << eta_refinement;
   if ((size_t)ipow(nl, P.dim) != n) return fail(ctx, SLOD_ERR_INVALID, "coefficient table size != (2^r)^dim");
-  if (nl > P.nsub)
-    return fail(ctx, SLOD_ERR_UNSUPPORTED,
-                "coefficient grid finer than the fine sub-cells (eta < h): not constant per sub-cell");
-  const int ratio = P.nsub / nl;  // power of two
-  std::vector<double> fine(ctx->coef_field_elems);
-  const int ns = P.nsub;
-  const int nz = (P.dim == 3) ? ns : 1;
-  for (int z = 0; z < nz; ++z)
-    for (int y = 0; y < ns; ++y)
-      for (int x = 0; x < ns; ++x)
-        fine[((size_t)z * ns + y) * ns + x] = cellwise[((size_t)(z / ratio) * nl + (y / ratio)) * nl + (x / ratio)];
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(ctx->d_coef + (size_t)field * ctx->coef_field_elems, fine.data(), sizeof(double) * fine.size(),
-                cudaMemcpyHostToDevice));
+  ctx->coef_table[field].assign(cellwise, cellwise + n);
+  ctx->coef_r[field] = eta_refinement;
   ctx->coef_set[field] = true;
+  ctx->coef_dirty = true;
   ctx->basis_done = ctx->coarse_done = false;
   return SLOD_OK;
 }
@@ -856,8 +901,8 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   if (rc) return rc;
   NEED_DEVICE();
   CK(cudaSetDevice(ctx->device));
-  for (int f = 0; f < ctx->n_fields; ++f)
-    if (!ctx->coef_set[f]) return fail(ctx, SLOD_ERR_STATE, "coefficient field not set");
+  rc = prepare_coefficients(ctx);
+  if (rc) return rc;
   rc = ensure_workspace(ctx, 1);
   if (rc) return rc;
   CK(upload_params(ctx->P));

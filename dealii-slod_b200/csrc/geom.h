@@ -32,6 +32,11 @@ struct Params {
   // reference sub-cell matrices, local dof = s * (lx + 2 ly + 4 lz) + comp
   double Kref[kMaxLocal * kMaxLocal];   // diffusion: Laplace * h^(d-2);  elasticity: 2 eps:eps
   double Klam[kMaxLocal * kMaxLocal];   // elasticity: div div
+  // coefficient finer than the sub-cells (eta < h, e.g. tests/Poisson_LOD_Example): one value per Gauss
+  // point of QIterated(QGauss<1>(2), n) and the per-Gauss-point matrices (q = qx + 2 qy + 4 qz)
+  int gauss_coef;
+  double Kq[kMaxLocal][kMaxLocal * kMaxLocal];
+  double Klamq[kMaxLocal][kMaxLocal * kMaxLocal];
 };
 
 struct Geom {
@@ -189,10 +194,20 @@ SLOD_HD double stiff_entry(const Params &P, const Geom &g, const CoefT *coef, co
         const int la = (a[0] - ox) + 2 * (a[1] - oy) + ((P.dim == 3) ? 4 * (a[2] - oz) : 0);
         const int lb = (a[0] + dl[0] - ox) + 2 * (a[1] + dl[1] - oy) + ((P.dim == 3) ? 4 * (a[2] + dl[2] - oz) : 0);
         const int idx = (la * P.s + ca) * nl + (lb * P.s + cb);
-        if (P.problem == 0)
-          acc += (double)coef[sc] * P.Kref[idx];
-        else
-          acc += (double)coef[nsubp + sc] * P.Kref[idx] + (double)coef[sc] * P.Klam[idx];
+        if (!P.gauss_coef) {
+          if (P.problem == 0)
+            acc += (double)coef[sc] * P.Kref[idx];
+          else
+            acc += (double)coef[nsubp + sc] * P.Kref[idx] + (double)coef[sc] * P.Klam[idx];
+        } else {
+          const int nq = 1 << P.dim;
+          for (int q = 0; q < nq; ++q) {
+            if (P.problem == 0)
+              acc += (double)coef[sc * nq + q] * P.Kq[q][idx];
+            else
+              acc += (double)coef[(nsubp + sc) * nq + q] * P.Kq[q][idx] + (double)coef[sc * nq + q] * P.Klamq[q][idx];
+          }
+        }
       }
   return acc;
 }

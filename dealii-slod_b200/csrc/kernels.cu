@@ -36,16 +36,19 @@ __device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, doub
   const long long nsub = cP.nsub;
   const long long fstride = (cP.dim == 3) ? nsub * nsub * nsub : nsub * nsub;
   const int nf = nfields();
-  for (int idx = threadIdx.x; idx < nf * nsubp; idx += blockDim.x) {
-    const int f = idx / nsubp;
-    int r = idx - f * nsubp;
+  const int nq = cP.gauss_coef ? (1 << cP.dim) : 1;   // values per sub-cell
+  for (int idx = threadIdx.x; idx < nf * nsubp * nq; idx += blockDim.x) {
+    const int q = idx % nq;
+    int r = idx / nq;
+    const int f = r / nsubp;
+    r -= f * nsubp;
     const int ox = r % msx;
     r /= msx;
     const int oy = r % msy;
     const int oz = r / msy;
     const long long gx = (long long)g.clo[0] * n + ox, gy = (long long)g.clo[1] * n + oy,
                     gz = (cP.dim == 3) ? (long long)g.clo[2] * n + oz : 0;
-    sCoef[idx] = d_coef[f * fstride + (gz * nsub + gy) * nsub + gx];
+    sCoef[idx] = d_coef[(f * fstride + (gz * nsub + gy) * nsub + gx) * nq + q];
   }
 }
 
@@ -154,7 +157,7 @@ k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__res
         for (int idx = lane; idx < NB * NB; idx += 32) {
           const int i = idx / NB, j = idx % NB;
           double v = 0.0;
-          if (i < nb && j <= i) v = sW[((c0 + i) % R) * ldw + (j - i + bw)];
+          if (i < nb && j <= i && i - j <= bw) v = sW[((c0 + i) % R) * ldw + (j - i + bw)];
           sLd[idx] = v;
           sLinv[idx] = 0.0;
         }
@@ -339,15 +342,24 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
       sM[row * ncd + col] = acc * scale;
     }
     // boundary dof list (order irrelevant for BD^T BD)
-    if (g.slod) {
-      for (int node = tid; node < g.nnodes; node += NT) {
-        int a[3];
-        node_coords(g, node, a);
-        if (node_class(cP, g, a) & 1) {
-          const int pos = atomicAdd(&sNb, s);
+    if (g.slod && tid < 32) {  // ascending order (deterministic summation order of BD^T BD)
+      int count = 0;
+      for (int base = 0; base < g.nnodes; base += 32) {
+        const int node = base + tid;
+        bool isb = false;
+        if (node < g.nnodes) {
+          int a[3];
+          node_coords(g, node, a);
+          isb = (node_class(cP, g, a) & 1) != 0;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, isb);
+        if (isb) {
+          const int pos = (count + __popc(mask & ((1u << tid) - 1u))) * s;
           for (int c = 0; c < s; ++c) sBlist[pos + c] = node * s + c;
         }
+        count += __popc(mask);
       }
+      if (tid == 0) sNb = count * s;
     }
     __syncthreads();
 
@@ -597,7 +609,10 @@ k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__re
         if (sOff <= tol) { ++sweeps; break; }
       }
       // eigenvalues, order by descending |lambda| (LAPACK singular value order), ghat = V^T g
-      for (int i = tid; i < n; i += NT) slam[i] = sG[i * (i + 1) / 2 + i];
+      for (int i = tid; i < n; i += NT) {
+        slam[i] = sG[i * (i + 1) / 2 + i];
+        sord[i] = i;  // stays a valid permutation even if NaNs break the ranking below
+      }
       __syncthreads();
       for (int i = tid; i < n; i += NT) {
         const double li = fabs(slam[i]);
@@ -606,7 +621,7 @@ k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__re
           const double lj = fabs(slam[j]);
           rank += (lj > li) || (lj == li && j < i);
         }
-        sord[rank] = i;
+        if (li == li) sord[rank] = i;
         double acc = 0.0;
         for (int r = 0; r < n; ++r) acc += sV[r * n + i] * sg[r];
         sgh[i] = acc;

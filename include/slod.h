@@ -73,8 +73,8 @@ const char *slod_last_create_error(void);
 
 /* coefficients: replaces problem_parameter (include/Diffusion.h:7-54).  `cellwise` holds one value
  * per cell of a (2^eta_refinement)^dim grid, lexicographic x fastest.  field 0 = alpha | lambda,
- * field 1 = mu.  Requires 2^eta_refinement <= 2^n_global_refinements * n_subdivisions (the table is
- * then constant on every fine sub-cell, as in all reference configurations). */
+ * field 1 = mu.  If the table is finer than the fine sub-cells (eta < h, as in tests/Poisson_LOD_Example)
+ * it is sampled at the Gauss points like the reference does; that mode is available in 2-D. */
 int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const double *cellwise, size_t n);
 
 /* integer maps (bit-exact with the reference / the oracle) -----------------------------------------*/

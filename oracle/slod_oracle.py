@@ -633,11 +633,12 @@ class SlodOracle:
         C = sp.csc_matrix((np.concatenate(v_phi), (rows, cols)), shape=(n_fine, n_coarse))
         AC = sp.csc_matrix((np.concatenate(v_aphi), (rows, cols)), shape=(n_fine, n_coarse))
         ones = sp.csc_matrix((np.ones(rows.shape), (rows, cols)), shape=(n_fine, n_coarse))
-        K = (C.T @ AC).tocsr()
-        pattern = (ones.T @ ones).tocsr()
-        pattern.data[:] = 0.0
-        K = (K + pattern).tocsr()           # keep structural zeros
-        K.sort_indices()
+        Kv = (C.T @ AC).tocsr()
+        pattern = (ones.T @ ones).tocsr()   # structural product pattern (explicit zeros of C are entries)
+        pattern.sort_indices()
+        r, c = pattern.nonzero()
+        K = sp.csr_matrix((np.asarray(Kv[r, c]).ravel(), pattern.indices.copy(), pattern.indptr.copy()),
+                          shape=pattern.shape)
         return K, C, AC
 
     # -- fine right-hand side used by Poisson_LOD_Example (f = 1, zero Dirichlet rows) ------------

@@ -1,9 +1,11 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
 
-Tolerances (fp64): every stage up to the Gram matrix is compared at 1e-10 relative; the selected basis at
-1e-10 where the reference's own selection is well conditioned and at c*eps*cond_eff elsewhere, because the
-reference solves the selection through the Gram matrix with a thresholded SVD (source/LOD.cc:656-725) and two
-correct fp64 implementations differ by that much; integer maps bit-exact."""
+Tolerances (fp64): every stage up to the Gram matrix is compared at 1e-10 relative on every case; the selected
+basis and A*basis at 1e-10 wherever that is reachable, and otherwise (boundary-touching patches, where the
+reference's Gram/thresholded-SVD/truncation rule, source/LOD.cc:656-725, is ill conditioned) at 50x the
+change a 4-ulp perturbation of the Gram matrix causes in the ORACLE's own answer -- no fp64 implementation
+can agree better than that.  Truncation step counts must agree exactly.
+Integer maps and the CSR pattern are bit-exact."""
 import os
 import re
 import sys
@@ -12,7 +14,8 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
-from parity_common import (EPS, build_pair, cond_eff, margin_safe, patch_tolerance, pkg)  # noqa: E402
+from parity_common import (EPS, build_pair, cond_eff, margin_safe, patch_tolerance, pkg,  # noqa: E402
+                           selection_sensitivity)
 from oracle.slod_oracle import GlibcRand, reference_random_table  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -87,12 +90,16 @@ def test_basis_and_coarse_matrix(case):
             if not margin_safe(res.info, d):
                 tol_of[(res.pid, d)] = None     # decision within rounding of flipping: not comparable
                 continue
-            tol = patch_tolerance(res.info, d)
+            err = np.linalg.norm(phi - res.basis[d])
+            tol = 1e-10
+            if err > tol and res.info["slod"]:
+                # ill-conditioned selection: the floor is what a few-ulp perturbation of G does to the oracle
+                tol = max(tol, 50.0 * selection_sensitivity(res.info, d))
             tol_of[(res.pid, d)] = tol
             n_checked_tight += tol == 1e-10
             if res.info["slod"]:
                 assert int(dg[1]) == res.info["trunc_steps"][d], (res.pid, d)
-            assert np.linalg.norm(phi - res.basis[d]) <= tol, (res.pid, d, cond_eff(res.info, d) if res.info["slod"] else 1)
+            assert err <= tol, (res.pid, d, err, tol, cond_eff(res.info, d) if res.info["slod"] else 1)
             nrm = np.linalg.norm(res.basis_premultiplied[d])
             assert np.linalg.norm(aphi - res.basis_premultiplied[d]) <= 10 * tol * nrm, (res.pid, d)
     assert n_checked_tight > 0
@@ -115,17 +122,42 @@ def test_basis_and_coarse_matrix(case):
         assert np.abs(val - K.data)[tight].max() <= 4e-9 * kmax
 
 
-def test_linearity_in_coefficient_scaling():
-    """Size-independent property: scaling alpha by c leaves phi unchanged and scales A phi and K by c."""
-    ctx1, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, kind="uniform100", seed=5)
-    tabs = [4.0 * t for t in __import__("parity_common").make_tables(2, 1, 5, "uniform100", 5)]
-    ctx2, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, tables=tabs, r=5)
+def test_scaling_by_power_of_two_is_exact():
+    """Size-independent property: scaling alpha by 4 (exact in binary floating point) leaves phi bit-identical
+    and scales A phi and K by exactly 4 -- also a determinism check (no atomics-ordered sums)."""
+    import parity_common
+    tabs1 = parity_common.make_tables(2, 1, 5, "uniform100", 5)
+    ctx1, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, tables=tabs1, r=5)
+    ctx2, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, tables=[4.0 * t for t in tabs1], r=5)
     for c in (ctx1, ctx2):
         c.compute_basis()
         c.assemble_coarse()
     p1, a1 = ctx1.all_basis()
     p2, a2 = ctx2.all_basis()
-    for pid in range(ctx1.n_patches):
-        if ctx1.diagnostics(pid)[1] == 0 and ctx1.diagnostics(pid)[0] < 0.45:
-            assert np.abs(p1[pid] - p2[pid]).max() < 1e-9
-            assert np.abs(4.0 * a1[pid] - a2[pid]).max() < 1e-9 * np.abs(a2[pid]).max()
+    assert np.array_equal(p1, p2)
+    assert np.array_equal(4.0 * a1, a2)
+    assert np.array_equal(4.0 * ctx1.coarse_csr()[2], ctx2.coarse_csr()[2])
+
+
+def test_partition_of_patches_matches_full_run():
+    """Patches are independent: computing two halves separately (the multi-GPU partition) gives the same basis."""
+    import torch
+    ctx, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, seed=9)
+    ctx.compute_basis()
+    p_full, a_full = ctx.all_basis()
+    n, s, stride = ctx.n_patches, 1, ctx.basis_stride
+    phi = torch.zeros((n, s, stride), dtype=torch.float64, device="cuda")
+    aphi = torch.zeros_like(phi)
+    ctx.compute_basis_device(0, n // 3, phi.data_ptr(), aphi.data_ptr())
+    ctx.compute_basis_device(n // 3, n, phi.data_ptr(), aphi.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(phi.cpu().numpy(), p_full)
+    assert np.array_equal(aphi.cpu().numpy(), a_full)
+    K = torch.zeros((n * s, ctx.ell_width), dtype=torch.float64, device="cuda")
+    ctx.assemble_coarse_device(0, n // 2, phi.data_ptr(), aphi.data_ptr(), K.data_ptr())
+    ctx.assemble_coarse_device(n // 2, n, phi.data_ptr(), aphi.data_ptr(), K.data_ptr())
+    torch.cuda.synchronize()
+    ctx.assemble_coarse()
+    rowptr, col, val = ctx.ell_to_csr(K.cpu().numpy())
+    r2, c2, v2 = ctx.coarse_csr()
+    assert np.array_equal(rowptr, r2) and np.array_equal(col, c2) and np.array_equal(val, v2)

@@ -70,3 +70,38 @@ def margin_safe(info, d):
     if not info.get("slod", False):
         return True
     return abs(info["dinf"][d] - 0.5) > 1e-3
+
+
+def selection_from_G(G, Minv, X, d, s_dim=None):
+    """The reference's selection (source/LOD.cc:637-752) restated on given stage matrices; returns the
+    interior part of the normalised basis function."""
+    ncd = G.shape[0]
+    other = [k for k in range(ncd) if k != d]
+    Go = G[np.ix_(other, other)]
+    g = G[other, d]
+    U, sig, Vt = np.linalg.svd(Go)
+    winv = np.where(sig > 1e-15 * sig[0], 1.0 / np.where(sig > 0, sig, 1.0), 0.0)
+    d_i = -(Vt.T @ (winv * (U.T @ g)))
+    for i in range(len(other) - 1, -1, -1):
+        if np.abs(d_i).max() < 0.5:
+            break
+        d_i = d_i + Vt[i, :] * (U[:, i] @ g) * winv[i]
+    c = Minv[:, d].copy()
+    for idx, k in enumerate(other):
+        c += d_i[idx] * Minv[:, k]
+    phi = X @ c
+    return phi / np.linalg.norm(phi)
+
+
+def selection_sensitivity(info, d, trials=4, rel=4 * EPS, seed=0):
+    """Change of the selected basis under a few-ulp symmetric perturbation of the Gram matrix: the accuracy
+    floor of ANY fp64 implementation of the reference's Gram/SVD selection on this patch."""
+    G, Minv, X = info["G"], info["Minv"], info["X"]
+    base = selection_from_G(G, Minv, X, d)
+    rs = np.random.default_rng(seed)
+    worst = 0.0
+    for _ in range(trials):
+        E = rs.standard_normal(G.shape)
+        E = (E + E.T) * 0.5 * rel * np.abs(G).max()
+        worst = max(worst, np.linalg.norm(selection_from_G(G + E, Minv, X, d) - base))
+    return worst
