@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the SLOD offline phase (BASELINE.json metric: SLOD basis patches/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the hot path over the whole synthetic problem: per-patch basis computation
+(source/LOD.cc:296-768) for every patch, then the coarse stiffness matrix (source/LOD.cc:860-973).
+Default workload: the configuration the metric is quoted on -- 3-D diffusion, 32^3 = 2^15 coarse cells,
+oversampling 2, 2 subdivisions, uniform random coefficient in [1, 1e4] on the fine sub-cell grid (SURVEY 8d,
+cfg 4a/5).  N > 1 (torchrun): contiguous Morton ranges of patches per rank, one NCCL all-gather of A*phi before
+the coarse matrix and one of the K row blocks after it; timing = max over ranks of CUDA-event time.
+
+value : patches/s with the coefficient already resident in HBM (device-buffer entry points).
+e2e   : the same through the host-buffer C ABI (slod_set_coefficient -> slod_compute_basis ->
+        slod_assemble_coarse -> slod_get_coarse_csr + slod_get_all_basis), host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: dim, s, ref, n, ell, r, kind, seed
+    "diffusion3d_32c_l2_n2": dict(dim=3, s=1, ref=5, n=2, ell=2, r=6, kind="uniform1e4", seed=3001),
+    "diffusion3d_16c_l2_n2": dict(dim=3, s=1, ref=4, n=2, ell=2, r=5, kind="uniform1e4", seed=3001),
+    "diffusion2d_256c_l2_n2": dict(dim=2, s=1, ref=8, n=2, ell=2, r=8, kind="uniform100", seed=1234),
+    "elasticity2d_128c_l1_n2": dict(dim=2, s=2, ref=7, n=2, ell=1, r=6, kind="uniform100", seed=2001),
+    "diffusion2d_16c_l2_n2": dict(dim=2, s=1, ref=4, n=2, ell=2, r=5, kind="uniform100", seed=1234),
+}
+DEFAULT_WORKLOAD = "diffusion3d_32c_l2_n2"
+FP64_PEAK_TFLOPS = 37.2   # measured on this pool's B200 with tools/fp64_peak.cu (mma.sync m8n8k4 f64; DFMA 36.3)
+
+
+def make_tables(w):
+    rs = np.random.default_rng(w["seed"])
+    n = (2 ** w["r"]) ** w["dim"]
+    out = []
+    for f in range(1 if w["s"] == 1 else 2):
+        u = rs.random(n)
+        hi = 1e4 if w["kind"] == "uniform1e4" else 100.0
+        out.append(1.0 + (hi - 1.0) * u)
+    return out
+
+
+def patch_shapes(w):
+    """Per patch: Ni, bw, Ncd, Nb (vectorised closed forms of slod::make_geom)."""
+    dim, s, ref, n, ell = w["dim"], w["s"], w["ref"], w["n"], w["ell"]
+    N = 2 ** ref
+    c = np.arange(N)
+    lo = np.maximum(c - ell, 0)
+    hi = np.minimum(c + ell, N - 1)
+    m1 = hi - lo + 1
+    dl = (lo == 0).astype(int)
+    dh = (hi == N - 1).astype(int)
+    grids = np.meshgrid(*([np.arange(N)] * dim), indexing="ij")
+    m = [m1[g].ravel() for g in grids]
+    nob = [(m1 * n + 1 - (1 - dl) - (1 - dh))[g].ravel() for g in grids]
+    p = [mm * n + 1 for mm in m]
+    q = [pp - 2 for pp in p]
+    Ni = s * np.prod(q, axis=0)
+    Ncd = s * np.prod(m, axis=0)
+    nnodes = np.prod(p, axis=0)
+    Nb = s * (nnodes - np.prod(nob, axis=0))
+    nbw = (q[0] * q[1] + q[0] + 1) if dim == 3 else (q[0] + 1)
+    bw = np.minimum(s * nbw + s - 1, Ni - 1)
+    return dict(Ni=Ni.astype(float), bw=bw.astype(float), Ncd=Ncd.astype(float), Nb=Nb.astype(float),
+                Nf=(s * nnodes).astype(float))
+
+
+def flop_model(w):
+    """Algorithmic flops per kernel, summed over all patches (banded-solver model of SURVEY 8d)."""
+    sh = patch_shapes(w)
+    Ni, bw, Ncd, Nb, Nf = sh["Ni"], sh["bw"], sh["Ncd"], sh["Nb"], sh["Nf"]
+    st = 27.0 if w["dim"] == 3 else 9.0
+    s = w["s"]
+    solve = Ni * bw * bw + 4.0 * Ni * bw * Ncd
+    dense = 2.0 * Ncd ** 3 + 2.0 * Nb * st * s * Ncd + 2.0 * Nb * Ncd ** 2 + 2.0 * Nb * Ncd ** 2
+    select = s * 12.0 * (Ncd - 1) ** 3
+    finish = s * (2.0 * Ni * Ncd + 2.0 * Nf * st * s)
+    return dict(patch_solve=float(solve.sum()), patch_dense=float(dense.sum()), patch_select=float(select.sum()),
+                patch_finish=float(finish.sum()))
+
+
+class ClockSampler:
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, args=(index,), daemon=True)
+
+    def _run(self, index):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+_ORC = None
+
+
+def _orc_patch(pid):
+    res = _ORC.compute_patch(pid)
+    return float(res.basis[0] @ res.basis_premultiplied[0])
+
+
+def cpu_oracle_rate(w, tables, n_sample, cores):
+    """patches/s of the oracle port on `cores` processes over an evenly spread sample of patch ids.
+    The integer patch structures (the oracle's stand-in for deal.II's per-patch Triangulation/DoFHandler
+    set-up) are built before the clock starts and inherited by the forked workers."""
+    global _ORC
+    import multiprocessing as mp
+    import threadpoolctl
+    from oracle.slod_oracle import CoefficientTable, SlodOracle, SlodProblem, morton_decode
+    n_patches = (2 ** w["ref"]) ** w["dim"]
+    pids = [int(x) for x in np.linspace(0, n_patches - 1, n_sample).astype(np.int64)]
+    with threadpoolctl.threadpool_limits(1):   # one BLAS thread per worker: the pool already uses every core
+        prob = SlodProblem(dim=w["dim"], spacedim=w["s"], n_global_refinements=w["ref"], n_subdivisions=w["n"],
+                           oversampling=w["ell"], stabilize=True,
+                           problem="diffusion" if w["s"] == 1 else "elasticity",
+                           coefficients=[CoefficientTable(w["dim"], w["r"], t) for t in tables])
+        _ORC = SlodOracle(prob)
+        for pid in pids:
+            _ORC.shape_for(morton_decode(pid, w["dim"], w["ref"]))
+        ctxm = mp.get_context("fork")
+        with ctxm.Pool(cores) as pool:
+            pool.map(_orc_patch, pids[:cores], chunksize=1)   # start the workers, touch LAPACK once
+            t0 = time.perf_counter()
+            pool.map(_orc_patch, pids, chunksize=1)
+            dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    tables = make_tables(w)
+    per_step = max(cores * 32, 64)
+    rates = []
+    for it in range(args.warmup + args.steps):
+        rate, dt = cpu_oracle_rate(w, tables, per_step, cores)
+        if it >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates]) * 1e3)
+    line = {
+        "impl": "reference", "metric": "slod_basis_patches_per_s", "value": value, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(w, wname),
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} patches per step spread evenly over the {n_total(w)} patch ids; "
+                                   "numpy/scipy oracle (deal.II/Trilinos reference cannot be built here), one process per core"},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def n_total(w):
+    return (2 ** w["ref"]) ** w["dim"]
+
+
+def config_of(w, wname):
+    return {"workload": wname, "dim": w["dim"], "spacedim": w["s"], "coarse_cells_per_axis": 2 ** w["ref"],
+            "n_patches": n_total(w), "oversampling": w["ell"], "n_subdivisions": w["n"], "stabilize": True,
+            "coefficient": f"{w['kind']} on 2^{w['r']} cells/axis, PCG64 seed {w['seed']}",
+            "l2": "inputs/outputs per step (basis 2x, coarse matrix) exceed the 126 MB L2",
+            "parallelism": "patches"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, args.workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("dealii-slod_b200")
+    pkg.build_library()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    tables = make_tables(w)
+    ctx = pkg.SlodContext(dim=w["dim"], spacedim=w["s"], n_global_refinements=w["ref"], n_subdivisions=w["n"],
+                          oversampling=w["ell"], stabilize=True, problem=0 if w["s"] == 1 else 1, device=local)
+    for f, t in enumerate(tables):
+        ctx.set_coefficient(f, w["r"], t)
+    n, s, stride, ellw = ctx.n_patches, w["s"], ctx.basis_stride, ctx.ell_width
+    assert n % world == 0, "patch count must divide over the ranks"
+    p0, p1 = rank * (n // world), (rank + 1) * (n // world)
+    phi = torch.zeros((n, s, stride), dtype=torch.float64, device=dev)
+    aphi = torch.zeros_like(phi)
+    K = torch.zeros((n * s, ellw), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.compute_basis_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), stream)
+        tk = ctx.timings().copy()
+        if world > 1:
+            dist.all_gather_into_tensor(aphi.view(-1), aphi[p0:p1].reshape(-1))
+        ctx.assemble_coarse_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), stream)
+        tk[4] = ctx.timings()[4]
+        if world > 1:
+            dist.all_gather_into_tensor(K.view(-1), K[p0 * s:p1 * s].reshape(-1))
+        return tk
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ksum = np.zeros(8)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            ksum += step()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n / (ms_step * 1e-3)
+    kms = ksum / args.steps          # per-step kernel times of this rank (ms)
+
+    # ---- end to end through the host-buffer C ABI (rank-local share when N > 1) ----
+    e2e = None
+    if not args.no_e2e:
+        ctx2 = ctx if world == 1 else None
+        if ctx2 is not None:
+            def e2e_step():
+                for f, tb in enumerate(tables):
+                    ctx2.set_coefficient(f, w["r"], tb)
+                ctx2.compute_basis()
+                ctx2.assemble_coarse()
+                rowptr, col, val = ctx2.coarse_csr()
+                ph, _ = ctx2.all_basis()
+                return float(val[0] + ph[0, 0, 0])
+            e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = max(1, min(args.steps, 3))
+            for _ in range(reps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            h2d = sum(t_.size * 8 for t_ in tables) * (2 ** (w["dim"] * max(0, w["ref"] + int(np.log2(w["n"])) - w["r"])))
+            d2h = n * s * ellw * 8 + 2 * n * s * stride * 8
+            e2e = {"value": n / dt, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": dt * 1e3,
+                   "path": "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_coarse_csr+slod_get_all_basis"}
+
+    if rank == 0:
+        fm = flop_model(w)
+        names = ["patch_solve", "patch_dense", "patch_select", "patch_finish"]
+        share = (n // world) / n
+        kern = {}
+        for i, nm in enumerate(names):
+            if kms[i] > 0:
+                kern[nm] = {"ms": float(kms[i]), "tflops": fm[nm] * share / (kms[i] * 1e-3) / 1e12}
+        kern["coarse"] = {"ms": float(kms[4])}
+        dom = max(names, key=lambda nm: kms[names.index(nm)])
+        achieved = kern[dom]["tflops"]
+        roofline = {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe on B200)", "kernel": "k_" + dom,
+                    "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                    "traffic": None,
+                    "peak_source": "measured here by tools/fp64_peak.cu (MEASURED_PEAKS.json has no fp64 entry)",
+                    "flop_model": "banded Cholesky Ni*bw^2 + 4*Ni*bw*Ncd per patch (SURVEY 8d), summed over actual patch shapes",
+                    "kernels": kern}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            ns = max(cores * 32, 64)
+            rate, dt = cpu_oracle_rate(w, tables, ns, cores)
+            cpu = {"value": rate, "unit": "patches/s", "cores": cores, "kind": "port",
+                   "sample": f"{ns} patches spread evenly over the patch ids ({dt:.1f} s), numpy/scipy oracle, one process per core"}
+        line = {"metric": "slod_basis_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_of(w, args.workload), "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "offline_wall_ms": ms_step}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
