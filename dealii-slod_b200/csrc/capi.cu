@@ -5,6 +5,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -50,6 +51,9 @@ struct slod_ctx {
   int *d_ids = nullptr;
   double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr;
   int solve_grid = 0;
+  int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
+  int mma_threads = 0;
+  long long mma_lws_per_cta = 0;
   SolveLayout sl{};
   DenseLayout dl{};
   SelectLayout el{};
@@ -325,8 +329,13 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     const int nw = (int)std::min<size_t>(ctx->chunk, ids.size() - off);
     CK(cudaMemcpyAsync(ctx->d_ids, ids.data() + off, sizeof(int) * nw, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[0], st));
-    CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
-                          ctx->d_Lws, ctx->d_status, ctx->sl));
+    if (ctx->mma_variant >= 0)
+      CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw,
+                                ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx,
+                                ctx->sl.x_stride, ctx->mma_lws_per_cta));
+    else
+      CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+                            ctx->d_Lws, ctx->d_status, ctx->sl));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                           ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
@@ -568,6 +577,26 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   sl.lws_per_cta = (long long)steps_max * (kSolveNB * kSolveNB + bw_max * kSolveNB);
   ctx->smem_solve = sizeof(double) * ((size_t)coef_doubles + (size_t)sl.R * sl.ldw + (size_t)sl.R * sl.ldr +
                                       (size_t)sl.R * kSolveNB + 2 * kSolveNB * kSolveNB + (size_t)kSolveNB * sl.ldr);
+  // tensor-core solver when the window (RB blocks of 8 rows) and the coarse columns (NW warps x 8) fit a variant
+  {
+    const int rb_need = (bw_max + 8 + 7) / 8, nw_need = (P.NcdMax + 7) / 8;
+    int variant = -1, rbmax = 0, nw = 0;
+    if (rb_need <= 13 && nw_need <= 16 && (rb_need > 4 || nw_need > 8)) { variant = 0; rbmax = 13; nw = 16; }
+    else if (rb_need <= 4 && nw_need <= 4) { variant = 1; rbmax = 4; nw = 4; }
+    else if (rb_need <= 4 && nw_need <= 8) { variant = 2; rbmax = 4; nw = 8; }
+    if (getenv("SLOD_FORCE_SIMT_SOLVER")) variant = -1;
+    if (variant >= 0) {
+      ctx->mma_variant = variant;
+      ctx->mma_threads = 32 * nw;
+      sl.ldx = 8 * nw;
+      const int nip = ((P.NiMax + 7) / 8) * 8;
+      sl.x_stride = (long long)nip * sl.ldx;
+      ctx->mma_lws_per_cta = (long long)(nip / 8) * (64 + 8 * (rbmax - 1) * 8);
+      sl.lws_per_cta = std::max(sl.lws_per_cta, ctx->mma_lws_per_cta);
+      sl.threads = ctx->mma_threads;
+      ctx->smem_solve = solve_mma_smem(variant, coef_doubles);
+    }
+  }
   DenseLayout &dl = ctx->dl;
   dl.threads = big ? 512 : 128;
   dl.ncd_max = P.NcdMax; dl.nb_max = nb_max; dl.coef_doubles = coef_doubles; dl.ldx = sl.ldx;
@@ -908,7 +937,11 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   CK(upload_params(ctx->P));
   const int id = (int)patch;
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
-  CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
+  if (ctx->mma_variant >= 0)
+    CK(launch_patch_solve_mma(ctx->mma_variant, 1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws,
+                              ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta));
+  else
+    CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
   CK(launch_patch_dense(1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag,
                         ctx->d_status, ctx->dl));
   ctx->launches += 2;

@@ -286,6 +286,10 @@ k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__res
   }
 }
 
+}  // namespace slod
+#include "solve_mma.cuh"
+namespace slod {
+
 // ------------------------------------------------------------------------------------------------
 // k_patch_dense
 // ------------------------------------------------------------------------------------------------
@@ -834,6 +838,31 @@ cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int
   k_patch_solve<kSolveNB><<<grid, lay.threads, smem, st>>>(ids, n_work, coef, X, Lws, status, lay);
   return cudaGetLastError();
 }
+template <int RBMAX, int NW>
+static cudaError_t launch_mma_t(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                                double *X, double *Lws, int *status, const SolveMmaLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_solve_mma<RBMAX, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_solve_mma<RBMAX, NW><<<grid, 32 * NW, smem, st>>>(ids, n_work, coef, X, Lws, status, lay);
+  return cudaGetLastError();
+}
+size_t solve_mma_smem(int variant, int coef_doubles) {
+  const int RBMAX = (variant == 0) ? 13 : 4;
+  const int R = 8 * RBMAX, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * R * 8 + 64 + 128);
+}
+cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
+                                   const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
+                                   long long x_stride, long long lws_per_cta) {
+  SolveMmaLayout lay{coef_doubles, ldx, x_stride, lws_per_cta};
+  switch (variant) {
+    case 0: return launch_mma_t<13, 16>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
+    case 1: return launch_mma_t<4, 4>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
+    case 2: return launch_mma_t<4, 8>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay) {
