@@ -45,6 +45,7 @@ struct slod_ctx {
   // results owned by the handle (host-buffer API)
   double *d_phi = nullptr, *d_aphi = nullptr, *d_Kell = nullptr, *d_diag = nullptr;
   int *d_status = nullptr;
+  int *d_counter = nullptr;
   bool basis_done = false, coarse_done = false;
   // chunk workspaces
   int chunk = 0;
@@ -230,7 +231,7 @@ void free_dev(slod_ctx *c) {
     p = nullptr;
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
-  F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
+  F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
 }
 
 // Expand the caller's tables (problem_parameter::value, include/Diffusion.h:40-53) onto the fine sub-cell
@@ -293,6 +294,7 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   chunk = std::min<int64_t>(chunk, ctx->n_patches);
   ctx->chunk = (int)chunk;
   CK(cudaMalloc(&ctx->d_ids, sizeof(int) * chunk));
+  CK(cudaMalloc(&ctx->d_counter, sizeof(int) * 4));
   CK(cudaMalloc(&ctx->d_X, sizeof(double) * (size_t)ctx->sl.x_stride * chunk));
   CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
   CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
@@ -341,7 +343,7 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
                           ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(launch_patch_select(std::min(nw, ctx->grid_select), ctx->smem_select, st, ctx->d_ids, nw, ctx->d_Minv,
-                           ctx->d_G, ctx->d_cvec, ctx->d_diag, ctx->d_status, ctx->el));
+                           ctx->d_G, ctx->d_cvec, ctx->d_diag, ctx->d_status, ctx->d_counter, ctx->el));
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(launch_patch_finish(std::min(nw, ctx->grid_finish), ctx->smem_finish, st, ctx->d_ids, nw, ctx->d_coef,
                            ctx->d_X, ctx->d_cvec, d_phi, d_aphi, ctx->fl));
@@ -608,6 +610,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   SelectLayout &el = ctx->el;
   el.threads = big ? 512 : 128;
   el.ncd_max = P.NcdMax; el.m_stride = dl.m_stride;
+  el.fast_path = getenv("SLOD_NO_FAST_SELECT") ? 0 : 1;
   ctx->smem_select = sizeof(double) * ((size_t)P.NcdMax * (P.NcdMax + 1) / 2 + (size_t)P.NcdMax * P.NcdMax +
                                        6 * (size_t)P.NcdMax) + sizeof(int) * (3 * (size_t)P.NcdMax + 8);
   FinishLayout &fl = ctx->fl;

@@ -477,7 +477,7 @@ __device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 
 __global__ void __launch_bounds__(512, 1)
 k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ Minv_in,
                const double *__restrict__ G_in, double *__restrict__ cvec, double *__restrict__ diag,
-               int *__restrict__ status, SelectLayout lay) {
+               int *__restrict__ status, int *__restrict__ work_counter, SelectLayout lay) {
   extern __shared__ double smem[];
   const int nmax = lay.ncd_max;       // >= n + 1
   double *sG = smem;                                   // packed lower, n(n+1)/2
@@ -496,7 +496,13 @@ k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__re
   __shared__ int sFlag;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
 
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  __shared__ int sWork;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sWork = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int w = sWork;
+    if (w >= n_work) break;
     const int pid = patch_ids[w];
     const Geom g = make_geom(cP, pid);
     const int ncd = g.Ncd, s = cP.s;
@@ -512,6 +518,72 @@ k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__re
         continue;
       }
       const int n = ncd - 1;               // considered_candidates
+      // ---- fast path: if no singular value is thresholded and the truncation loop does not fire, the
+      // reference's d = -G^+ g (source/LOD.cc:667-671) is the solution of the SPD system G d = -g: Cholesky in
+      // shared memory.  Any doubt (tiny pivot, ||d||_inf close to or above 0.5) goes to the eigen-solver. ----
+      if (lay.fast_path) {
+        double *Lc = sV;  // [n][n] full storage, lower part used
+        for (int idx = tid; idx < n * n; idx += NT) {
+          const int i = idx / n, j = idx % n;
+          Lc[idx] = (j <= i) ? Gf[(i + (i >= d)) * ncd + (j + (j >= d))] : 0.0;
+        }
+        for (int i = tid; i < n; i += NT) { sg[i] = Gf[(i + (i >= d)) * ncd + d]; sd[i] = -sg[i]; }
+        if (tid == 0) sFlag = 0;
+        __syncthreads();
+        double dmax = 0.0, pmin = 1e300;
+        for (int i = 0; i < n; ++i) dmax = fmax(dmax, Lc[i * n + i]);
+        for (int k = 0; k < n; ++k) {
+          __syncthreads();
+          const double akk = Lc[k * n + k];   // stays untouched during this step; sqrt kept in slam[k]
+          pmin = fmin(pmin, akk);
+          const double inv = 1.0 / sqrt(akk);
+          for (int i = k + 1 + tid; i < n; i += NT) Lc[i * n + k] *= inv;
+          if (tid == 0) slam[k] = akk * inv;
+          __syncthreads();
+          const int m = n - k - 1;
+          for (int idx = tid; idx < m * m; idx += NT) {
+            const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            if (j <= i) Lc[i * n + j] -= Lc[i * n + k] * Lc[j * n + k];
+          }
+        }
+        __syncthreads();
+        const bool spd_ok = (pmin > 1e-12 * dmax);
+        if (spd_ok && warp == 0) {
+          // L z = -g, then L^T x = z ; one warp, column-oriented updates
+          for (int k = 0; k < n; ++k) {
+            const double zk = sd[k] / slam[k];
+            __syncwarp();
+            if (lane == 0) sd[k] = zk;
+            for (int i = k + 1 + lane; i < n; i += 32) sd[i] -= Lc[i * n + k] * zk;
+            __syncwarp();
+          }
+          for (int k = n - 1; k >= 0; --k) {
+            const double xk = sd[k] / slam[k];
+            __syncwarp();
+            if (lane == 0) sd[k] = xk;
+            for (int j = lane; j < k; j += 32) sd[j] -= Lc[k * n + j] * xk;
+            __syncwarp();
+          }
+          double m = 0.0;
+          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sd[r]));
+          m = warp_max(m);
+          if (lane == 0) {
+            if (m < 0.49) {
+              sFlag = 1;
+              dg[0] = m; dg[1] = 0; dg[2] = dmax; dg[3] = pmin; dg[5] = 1; dg[6] = 0;
+            }
+          }
+        }
+        __syncthreads();
+        if (sFlag) {
+          for (int i = tid; i < ncd; i += NT) {
+            double acc = Minv[i * ncd + d];
+            for (int k = 0; k < n; ++k) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
+            cv[i] = acc;
+          }
+          continue;
+        }
+      }
       const int np = (n + 1) & ~1;         // even player count for the tournament
       const int half = np / 2;
       // other_phi: all coarse dofs but d  (source/LOD.cc:637-640)
@@ -872,10 +944,13 @@ cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int
   return cudaGetLastError();
 }
 cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
-                                const double *G, double *cvec, double *diag, int *status, const SelectLayout &lay) {
+                                const double *G, double *cvec, double *diag, int *status, int *work_counter,
+                                const SelectLayout &lay) {
   cudaError_t e = cudaFuncSetAttribute(k_patch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_patch_select<<<grid, lay.threads, smem, st>>>(ids, n_work, Minv, G, cvec, diag, status, lay);
+  e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  k_patch_select<<<grid, lay.threads, smem, st>>>(ids, n_work, Minv, G, cvec, diag, status, work_counter, lay);
   return cudaGetLastError();
 }
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,

@@ -29,6 +29,7 @@ struct DenseLayout {
 };
 struct SelectLayout {
   int threads;
+  int fast_path;  // try the Cholesky solve of G d = -g before the eigen-solver
   int ncd_max;
   long long m_stride;
 };
@@ -52,7 +53,8 @@ cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);
 cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
-                                const double *G, double *cvec, double *diag, int *status, const SelectLayout &lay);
+                                const double *G, double *cvec, double *diag, int *status, int *work_counter,
+                                const SelectLayout &lay);
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                 const double *X, const double *cvec, double *phi, double *aphi,
                                 const FinishLayout &lay);
