@@ -52,6 +52,7 @@ struct slod_ctx {
   int *d_ids = nullptr;
   double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr;
   int solve_grid = 0;
+  int dense_ntile = 0;   // 0: generic SIMT dense stage, else tensor-core variant
   int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
   int mma_threads = 0;
   long long mma_lws_per_cta = 0;
@@ -339,8 +340,12 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
       CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Lws, ctx->d_status, ctx->sl));
     CK(cudaEventRecord(ctx->ev[1], st));
-    CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
-                          ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+    if (ctx->dense_ntile)
+      CK(launch_patch_dense_mma(ctx->dense_ntile, std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw,
+                                ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+    else
+      CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+                            ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
     CK(cudaEventRecord(ctx->ev[2], st));
     CK(launch_patch_select(std::min(nw, ctx->grid_select), ctx->smem_select, st, ctx->d_ids, nw, ctx->d_Minv,
                            ctx->d_G, ctx->d_cvec, ctx->d_diag, ctx->d_status, ctx->d_counter, ctx->el));
@@ -607,6 +612,19 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   ctx->smem_dense = sizeof(double) * ((size_t)coef_doubles + (size_t)dl.m_stride + 2 * 16 * (size_t)P.NcdMax +
                                       2 * (size_t)P.NcdMax + 16 * 54) +
                     sizeof(int) * (16 * 54 + (size_t)nb_max + 8);
+  {
+    const int nt_need = (P.NcdMax + 7) / 8;
+    int ntile = nt_need <= 4 ? 4 : (nt_need <= 8 ? 8 : (nt_need <= 16 ? 16 : 0));
+    if (getenv("SLOD_FORCE_SIMT_DENSE")) ntile = 0;
+    if (ntile) {
+      const size_t sm = dense_mma_smem(ntile, coef_doubles, nb_max);
+      if (sm <= prop.sharedMemPerBlockOptin) {
+        ctx->dense_ntile = ntile;
+        ctx->smem_dense = sm;
+        dl.threads = 32 * ntile;
+      }
+    }
+  }
   SelectLayout &el = ctx->el;
   el.threads = big ? 512 : 128;
   el.ncd_max = P.NcdMax; el.m_stride = dl.m_stride;
@@ -945,8 +963,12 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
                               ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta));
   else
     CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
-  CK(launch_patch_dense(1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag,
-                        ctx->d_status, ctx->dl));
+  if (ctx->dense_ntile)
+    CK(launch_patch_dense_mma(ctx->dense_ntile, 1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv,
+                              ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+  else
+    CK(launch_patch_dense(1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag,
+                          ctx->d_status, ctx->dl));
   ctx->launches += 2;
   CK(cudaDeviceSynchronize());
   const Geom g = make_geom(ctx->P, id);

@@ -469,6 +469,10 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
   }
 }
 
+}  // namespace slod
+#include "dense_mma.cuh"
+namespace slod {
+
 // ------------------------------------------------------------------------------------------------
 // k_patch_select : thresholded pseudo-inverse through a cyclic Jacobi eigen-solver
 // ------------------------------------------------------------------------------------------------
@@ -943,6 +947,31 @@ cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int
   k_patch_dense<<<grid, lay.threads, smem, st>>>(ids, n_work, coef, X, Minv, G, diag, status, lay);
   return cudaGetLastError();
 }
+template <int NTILE>
+static cudaError_t launch_dense_t(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                                  const double *X, double *Minv, double *G, double *diag, int *status,
+                                  const DenseLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_dense_mma<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_dense_mma<NTILE><<<grid, 32 * NTILE, smem, st>>>(ids, n_work, coef, X, Minv, G, diag, status, lay);
+  return cudaGetLastError();
+}
+size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
+  const int NC = 8 * ntile, LDM = NC + 4;
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 2 * NC + kDTB * 54) +
+         sizeof(int) * ((size_t)kDTB * 54 + nb_max + 8);
+}
+cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
+                                   const double *coef, const double *X, double *Minv, double *G, double *diag,
+                                   int *status, const DenseLayout &lay) {
+  switch (ntile) {
+    case 4: return launch_dense_t<4>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
+    case 8: return launch_dense_t<8>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
+    case 16: return launch_dense_t<16>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
                                 const double *G, double *cvec, double *diag, int *status, int *work_counter,
                                 const SelectLayout &lay) {

@@ -52,6 +52,11 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);
+// tensor-core dense stage, ntile in {4, 8, 16} (8*ntile >= coarse dofs per patch)
+size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max);
+cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
+                                   const double *coef, const double *X, double *Minv, double *G, double *diag,
+                                   int *status, const DenseLayout &lay);
 cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
                                 const double *G, double *cvec, double *diag, int *status, int *work_counter,
                                 const SelectLayout &lay);
