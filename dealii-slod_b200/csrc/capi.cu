@@ -55,6 +55,7 @@ struct slod_ctx {
   int dense_ntile = 0;   // 0: generic SIMT dense stage, else tensor-core variant
   int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
   int mma_threads = 0;
+  int mma_nip = 0, mma_stw = 0;
   long long mma_lws_per_cta = 0;
   SolveLayout sl{};
   DenseLayout dl{};
@@ -335,7 +336,7 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     if (ctx->mma_variant >= 0)
       CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx,
-                                ctx->sl.x_stride, ctx->mma_lws_per_cta));
+                                ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw));
     else
       CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Lws, ctx->d_status, ctx->sl));
@@ -601,7 +602,9 @@ int slod_create(const slod_params *par, slod_ctx **out) {
       ctx->mma_lws_per_cta = (long long)(nip / 8) * (64 + 8 * (rbmax - 1) * 8);
       sl.lws_per_cta = std::max(sl.lws_per_cta, ctx->mma_lws_per_cta);
       sl.threads = ctx->mma_threads;
-      ctx->smem_solve = solve_mma_smem(variant, coef_doubles);
+      ctx->mma_nip = nip;
+      ctx->mma_stw = P.s * ((P.dim == 3) ? 13 : 4) + P.s;
+      ctx->smem_solve = solve_mma_smem(variant, coef_doubles, ctx->mma_nip, ctx->mma_stw);
     }
   }
   DenseLayout &dl = ctx->dl;
@@ -960,7 +963,7 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
   if (ctx->mma_variant >= 0)
     CK(launch_patch_solve_mma(ctx->mma_variant, 1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws,
-                              ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta));
+                              ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw));
   else
     CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
   if (ctx->dense_ntile)

@@ -922,15 +922,18 @@ static cudaError_t launch_mma_t(int grid, size_t smem, cudaStream_t st, const in
   k_patch_solve_mma<RBMAX, NW><<<grid, 32 * NW, smem, st>>>(ids, n_work, coef, X, Lws, status, lay);
   return cudaGetLastError();
 }
-size_t solve_mma_smem(int variant, int coef_doubles) {
+size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw) {
   const int RBMAX = (variant == 0) ? 13 : 4;
+  const int NW = (variant == 0) ? 16 : (variant == 1 ? 4 : 8);
   const int R = 8 * RBMAX, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * R * 8 + 64 + 128);
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * R * 8 + 64 + 128 +
+                           (size_t)nip_max * stw) +
+         sizeof(int) * ((size_t)nip_max + 8 * NW + RBMAX * (RBMAX - 1) / 2 + 32 + 8);
 }
 cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
-                                   long long x_stride, long long lws_per_cta) {
-  SolveMmaLayout lay{coef_doubles, ldx, x_stride, lws_per_cta};
+                                   long long x_stride, long long lws_per_cta, int nip_max, int stw) {
+  SolveMmaLayout lay{coef_doubles, nip_max, stw, ldx, x_stride, lws_per_cta};
   switch (variant) {
     case 0: return launch_mma_t<13, 16>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
     case 1: return launch_mma_t<4, 4>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);

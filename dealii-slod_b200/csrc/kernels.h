@@ -45,10 +45,10 @@ cudaError_t upload_params(const Params &p);
 cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                double *X, double *Lws, int *status, const SolveLayout &lay);
 // tensor-core (mma.sync f64) solver; variant 0: <RBMAX 13, 16 warps> (3-D), 1: <4, 4 warps>, 2: <4, 8 warps> (2-D)
-size_t solve_mma_smem(int variant, int coef_doubles);
+size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw);
 cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
-                                   long long x_stride, long long lws_per_cta);
+                                   long long x_stride, long long lws_per_cta, int nip_max, int stw);
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);

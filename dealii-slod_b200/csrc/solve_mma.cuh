@@ -8,6 +8,7 @@
 // the trailing update of step k (look-ahead), so there are two block barriers per step.
 // Included by kernels.cu (needs cP and the helpers defined there).
 #pragma once
+#include <cuda_pipeline.h>
 
 namespace slod {
 
@@ -30,12 +31,14 @@ __device__ __forceinline__ double c_to_b(double c0, double c1, int lane, int j) 
 __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double *sLd, double *sLinv) {
   const int g = lane >> 2, t = lane & 3;
   int bad = 0;
+  double rdiag[8];  // 1 / L_kk
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const double sel = (k & 1) ? v1 : v0;
     const double dkk = __shfl_sync(0xffffffffu, sel, 4 * k + (k >> 1));
     if (!(dkk > 0.0)) bad = 1;
-    const double inv = 1.0 / sqrt(dkk);
+    const double inv = rsqrt(dkk);
+    rdiag[k] = inv;
     const double lik = __shfl_sync(0xffffffffu, sel, 4 * g + (k >> 1)) * inv;
     const double lc0 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t) + (k >> 1)) * inv;
     const double lc1 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t + 1) + (k >> 1)) * inv;
@@ -58,7 +61,7 @@ __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double 
 #pragma unroll
       for (int tt = 0; tt < 8; ++tt)
         if (tt < i) sum -= sLd[i * 8 + tt] * ((tt >= j) ? x[tt] : 0.0);
-      x[i] = (i >= j) ? sum / sLd[i * 8 + i] : 0.0;
+      x[i] = (i >= j) ? sum * rdiag[i] : 0.0;
       if (i >= j) sLinv[i * 8 + j] = x[i];
     }
   }
@@ -68,10 +71,24 @@ __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double 
 
 struct SolveMmaLayout {
   int coef_doubles;
+  int nip_max;            // interior dofs per patch rounded up to 8
+  int stw;                // lower-stencil entries per dof row: spacedim * (13 | 4) + spacedim
   int ldx;                // leading dimension of X rows (8 * NW)
   long long x_stride;     // doubles per patch in Xbuf (NiPmax * ldx)
   long long lws_per_cta;  // doubles of L workspace per CTA  (steps_max * (64 + 8*(RBMAX-1)*8))
 };
+
+// number of "lower" stencil nodes (linear offset < 0): 13 in 3-D, 4 in 2-D
+__device__ __forceinline__ int n_lower_nodes() { return cP.dim == 3 ? 13 : 4; }
+// e-th lower stencil node offset (dx,dy,dz); e == n_lower_nodes() is the node itself
+__device__ __forceinline__ void lower_offset(int e, int dl[3]) {
+  // enumeration of {-1,0,1}^dim in x-fastest order, truncated before the centre: e = (dx+1) + 3 (dy+1) + 9 (dz+1)
+  if (cP.dim == 3) {
+    dl[0] = e % 3 - 1; dl[1] = (e / 3) % 3 - 1; dl[2] = e / 9 - 1;
+  } else {
+    dl[0] = e % 3 - 1; dl[1] = e / 3 - 1; dl[2] = 0;
+  }
+}
 
 template <int RBMAX, int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
@@ -81,7 +98,9 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   constexpr int LDWF = (R % 16 == 8) ? R : R + 8;  // row stride with LDWF % 16 == 8 : conflict-free C fragments
   constexpr int LDP = R + 4;                        // k-major panel copy, LDP % 16 in {4, 12}
   constexpr int NT = 32 * NW;
+  constexpr int NC = 8 * NW;
   constexpr int LSTEP = 64 + 8 * (RBMAX - 1) * 8;  // doubles per step in the L workspace: Linv + panel rows
+  constexpr int NTT = RBMAX * (RBMAX - 1) / 2;
   extern __shared__ double smem[];
   double *sCoef = smem;
   double *sWf = sCoef + lay.coef_doubles;   // [R][LDWF] circular dense window of the trailing matrix
@@ -89,9 +108,21 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   double *sLpR = sLpT + 8 * LDP;            // [2][R*8]  panel rows (row-major by offset) for the backward pass
   double *sLd = sLpR + 2 * R * 8;           // [64] scratch
   double *sLinv = sLd + 64;                 // [2][64]
+  double *sSt = sLinv + 128;                // [nip_max][stw] lower stencil values of A_ii, one row per dof
+  int *sRowPk = (int *)(sSt + (size_t)lay.nip_max * lay.stw);  // [nip_max] packed node coords / comp / mask
+  int *sColCell = sRowPk + lay.nip_max;     // [NC] packed cell coords of each coarse column (or -1)
+  int *sTileTab = sColCell + NC;            // [NTT] (offI | offJ << 8) of the trailing-update tiles
+  int *sDOff = sTileTab + NTT;              // [32] dof offset of each lower stencil slot
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   double *myL = Lws + (size_t)blockIdx.x * lay.lws_per_cta;
+  const int sdim = cP.s, stw = lay.stw, nlow = n_lower_nodes();
+
+  for (int tt = tid; tt < NTT; tt += NT) {
+    int offI = 1;
+    while ((offI + 1) * offI / 2 <= tt) ++offI;
+    sTileTab[tt] = offI | ((tt - offI * (offI - 1) / 2 + 1) << 8);
+  }
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int pid = patch_ids[w];
@@ -105,40 +136,104 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     load_coef(geo, d_coef, sCoef);
     __syncthreads();
 
-    // value of A_ii[r][c] (c <= r inside the band, else 0); rows >= Ni are identity rows
-    auto a_entry = [&](int r, int c) -> double {
-      if (r >= Ni || c >= Ni) return (r == c) ? 1.0 : 0.0;
-      if (c > r || r - c > bw) return 0.0;
-      int a[3], b[3], ca, cb;
-      idof_to_node(geo, r, a, ca);
-      idof_to_node(geo, c, b, cb);
-      int dl[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
-      if (dl[0] < -1 || dl[0] > 1 || dl[1] < -1 || dl[1] > 1 || dl[2] < -1 || dl[2] > 1) return 0.0;
-      return stiff_entry(cP, geo, sCoef, a, dl, ca, cb);
-    };
-    // write the 8 rows of block `blk` (all live column slots) into its slot of the window
-    auto assemble_block = [&](int blk) {
-      const int slot = blk % RB;
-      const int first_col_blk = blk - (RB - 1);  // oldest block that can be live together with blk
-      for (int idx = tid; idx < 8 * 8 * RB; idx += NT) {
-        const int i = idx / (8 * RB), cs = idx % (8 * RB);  // row in block, column slot index
-        const int csb = cs >> 3;                            // column slot block
-        // absolute block of this column slot: the one in [first_col_blk, blk] congruent to csb mod RB
-        int cb_abs = first_col_blk + ((csb - (first_col_blk % RB + RB) % RB + RB) % RB);
-        double v = 0.0;
-        if (cb_abs >= 0) v = a_entry(8 * blk + i, 8 * cb_abs + (cs & 7));
-        sWf[(8 * slot + i) * LDWF + cs] = v;
-      }
-    };
-    // right-hand-side tile (C layout) of block blk for this warp's columns
-    auto rhs_tile = [&](int blk, double &c0, double &c1) {
-      const int r = 8 * blk + g, col = 8 * warp + 2 * t;
-      c0 = c1 = 0.0;
+    // ---- per-patch tables: the lower stencil row of every interior dof, packed coordinates, column cells ----
+    for (int r = tid; r < 8 * NBLK; r += NT) {
+      int pk = 0;
       if (r < Ni) {
         int a[3], ca;
         idof_to_node(geo, r, a, ca);
-        if (col < ncd) c0 = proj_entry(cP, geo, a, ca, col);
-        if (col + 1 < ncd) c1 = proj_entry(cP, geo, a, ca, col + 1);
+        int mask = 0;
+        for (int e = 0; e <= nlow; ++e) {
+          int dl[3];
+          lower_offset(e, dl);
+          int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
+          bool inside = true;
+          for (int x = 0; x < cP.dim; ++x) inside = inside && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
+          for (int cb = 0; cb < sdim; ++cb) {
+            const bool use = inside && (e < nlow || cb <= ca);
+            sSt[(size_t)r * stw + e * sdim + cb] = use ? stiff_entry(cP, geo, sCoef, a, dl, ca, cb) : 0.0;
+          }
+          if (inside) mask |= 1 << e;
+        }
+        pk = a[0] | (a[1] << 5) | (a[2] << 10) | (ca << 15) | (mask << 16) | (1 << 31);
+      }
+      sRowPk[r] = pk;
+    }
+    for (int col = tid; col < NC; col += NT) {
+      int v = -1;
+      if (col < ncd) {
+        int kc[3];
+        col_to_cell(cP, geo, col / sdim, kc);
+        v = kc[0] | (kc[1] << 5) | (kc[2] << 10) | ((col % sdim) << 15);
+      }
+      sColCell[col] = v;
+    }
+    if (tid <= nlow) {
+      int dl[3];
+      lower_offset(tid, dl);
+      sDOff[tid] = (dl[0] + geo.q[0] * (dl[1] + geo.q[1] * dl[2])) * sdim;
+    }
+    __syncthreads();
+
+    // write the 8 rows of block `blk` (slot sB) for all live column slots; entries outside the band are zero,
+    // rows >= Ni are identity rows.  One (row, column-slot-block) pair per thread, no divisions.
+    auto assemble_block = [&](int blk, int sB) {
+      for (int pair = tid; pair < 8 * RB; pair += NT) {
+        const int i = pair & 7, sb = pair >> 3;
+        int back = sB - sb;
+        if (back < 0) back += RB;
+        const int cb_abs = blk - back;  // absolute column block living in slot sb
+        const int r = 8 * blk + i;
+        double out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = 0.0;
+        const int pk = sRowPk[r];
+        if (pk < 0) {  // bit 31: a real dof row
+          const int ca = (pk >> 15) & 1, mask = (pk >> 16) & 0x7fff;
+          for (int e = 0; e <= nlow; ++e) {
+            if (!((mask >> e) & 1)) continue;
+            for (int cb = 0; cb < sdim; ++cb) {
+              if (e == nlow && cb > ca) continue;
+              const int c = r + sDOff[e] + (cb - ca);
+              if ((c >> 3) == cb_abs) {
+                const double v = sSt[(size_t)r * stw + e * sdim + cb];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                  if (cc == (c & 7)) out[cc] = v;
+              }
+            }
+          }
+        } else if (back == 0) {
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc)
+            if (cc == i) out[cc] = 1.0;
+        }
+        double2 *dst = reinterpret_cast<double2 *>(sWf + (8 * sB + i) * LDWF + 8 * sb);
+        dst[0] = make_double2(out[0], out[1]);
+        dst[1] = make_double2(out[2], out[3]);
+        dst[2] = make_double2(out[4], out[5]);
+        dst[3] = make_double2(out[6], out[7]);
+      }
+    };
+    // right-hand-side tile (C layout) of block blk for this warp's columns: P_i entries from the tables
+    auto rhs_tile = [&](int blk, double &c0, double &c1) {
+      c0 = c1 = 0.0;
+      const int pk = sRowPk[8 * blk + g];
+      if (pk >= 0) return;
+      const int ca = (pk >> 15) & 1;
+      const int n = cP.n;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = sColCell[8 * warp + 2 * t + h];
+        if (cc < 0 || ((cc >> 15) & 1) != ca) continue;
+        double wgt = cP.pw;
+        bool in = true;
+        for (int x = 0; x < cP.dim; ++x) {
+          const int tt = ((pk >> (5 * x)) & 31) - n * ((cc >> (5 * x)) & 31);
+          if (tt < 0 || tt > n) in = false;
+          if (tt != 0 && tt != n) wgt *= 2.0;
+        }
+        if (in) { if (h == 0) c0 = wgt; else c1 = wgt; }
       }
     };
 
@@ -148,7 +243,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       creg[sb][0] = creg[sb][1] = 0.0;
       if (sb < RB && sb < NBLK) rhs_tile(sb, creg[sb][0], creg[sb][1]);
     }
-    for (int b = 0; b < RB && b < NBLK; ++b) assemble_block(b);
+    for (int b = 0; b < RB && b < NBLK; ++b) assemble_block(b, b);
     __syncthreads();
     int bad = 0;
     if (warp == 0) {
@@ -158,8 +253,8 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
 
     // ============================ factorisation + forward substitution ============================
-    for (int k = 0; k < NBLK; ++k) {
-      const int kslot = k % RB, cur = k & 1;
+    for (int k = 0, kslot = 0; k < NBLK; ++k, kslot = (kslot + 1 == RB) ? 0 : kslot + 1) {
+      const int cur = k & 1;
       const double *Linv = sLinv + cur * 64;
       int nl = NBLK - 1 - k;  // live panel blocks below the diagonal block
       if (nl > RB - 1) nl = RB - 1;
@@ -197,12 +292,11 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       __syncthreads();
       // ---- S3: trailing update of the window (shared C), look-ahead factorisation, RHS tiles (register C) ----
       const int ntile = nl * (nl + 1) / 2;
-      for (int tt = warp; tt < ntile; tt += NW) {
-        // tt = offI (offI - 1) / 2 + offJ - 1
-        int offI = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)tt)) * 0.5f);
-        while (offI * (offI - 1) / 2 > tt) --offI;
-        while ((offI + 1) * offI / 2 <= tt) ++offI;
-        const int offJ = tt - offI * (offI - 1) / 2 + 1;
+      // warp 0 owns the look-ahead chain (next diagonal tile + its factorisation); the other tiles go round
+      // robin over warps 1..NW-1
+      for (int tt = (warp == 0) ? 0 : warp; tt < ntile; tt += (warp == 0) ? ntile : NW - 1) {
+        const int tab = sTileTab[tt];
+        const int offI = tab & 0xff, offJ = tab >> 8;
         int sI = kslot + offI, sJ = kslot + offJ;
         if (sI >= RB) sI -= RB;
         if (sJ >= RB) sJ -= RB;
@@ -231,7 +325,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       }
       // ---- slide: block k + RB takes the slot of block k ----
       if (k + RB < NBLK) {
-        assemble_block(k + RB);
+        assemble_block(k + RB, kslot);
         double n0, n1;
         rhs_tile(k + RB, n0, n1);
 #pragma unroll
@@ -251,15 +345,17 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       int nl = NBLK - 1 - k;
       if (nl > RB - 1) nl = RB - 1;
       double *dst = sLpR + buf * R * 8;
-      for (int idx = tid; idx < 64 + nl * 64; idx += NT) {
-        if (idx < 64) sLinv[buf * 64 + idx] = Ls[idx];
-        else dst[idx - 64] = Ls[idx];
+      for (int idx = tid; idx < 32 + nl * 32; idx += NT) {  // 16-byte pieces, asynchronous (LDGSTS)
+        double *d = (idx < 32) ? (sLinv + buf * 64 + 2 * idx) : (dst + 2 * (idx - 32));
+        __pipeline_memcpy_async(d, Ls + 2 * idx, 16);
       }
+      __pipeline_commit();
     };
     stage_step(NBLK - 1, (NBLK - 1) & 1);
+    __pipeline_wait_prior(0);
     __syncthreads();
-    for (int k = NBLK - 1; k >= 0; --k) {
-      const int kslot = k % RB, buf = k & 1;
+    for (int k = NBLK - 1, kslot = (NBLK - 1) % RB; k >= 0; --k, kslot = (kslot == 0) ? RB - 1 : kslot - 1) {
+      const int buf = k & 1;
       int nl = NBLK - 1 - k;
       if (nl > RB - 1) nl = RB - 1;
       if (k > 0) stage_step(k - 1, buf ^ 1);
@@ -290,6 +386,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
 #pragma unroll
       for (int sb = 0; sb < RBMAX; ++sb)
         if (sb == kslot) { xb[sb][0] = nb0; xb[sb][1] = nb1; }
+      __pipeline_wait_prior(0);
       __syncthreads();
     }
   }
