@@ -619,6 +619,8 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     const int nt_need = (P.NcdMax + 7) / 8;
     int ntile = nt_need <= 4 ? 4 : (nt_need <= 8 ? 8 : (nt_need <= 16 ? 16 : 0));
     if (getenv("SLOD_FORCE_SIMT_DENSE")) ntile = 0;
+    // the register/mma dense stage reads X rows with 16-byte loads: needs the padded layout of the mma solver
+    if (ntile && (ctx->mma_variant < 0 || 8 * ntile != sl.ldx)) ntile = 0;
     if (ntile) {
       const size_t sm = dense_mma_smem(ntile, coef_doubles, nb_max);
       if (sm <= prop.sharedMemPerBlockOptin) {

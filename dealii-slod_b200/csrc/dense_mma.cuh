@@ -1,12 +1,20 @@
-// k_patch_dense_mma : M, M^{-1}, BD = (S_b X - P_b) M^{-1} and G = BD^T BD with FP64 mma.sync tiles.
-// One CTA (NTILE warps) per patch; warp w owns the coarse-column tile [8w, 8w+8) of BD and two tile rows
-// (w and NTILE-1-w, lower triangle only) of the Gram matrix, whose accumulators stay in registers while the
-// boundary rows stream through shared memory in tiles of 32.  Included by kernels.cu.
+// k_patch_dense_mma : M, M^{-1}, BD = (S_b X - P_b) M^{-1} and G = BD^T BD.
+//
+// One CTA (NTILE warps) per patch.
+//  * M = P_i^T X / H^d is accumulated straight into a register tile (4 x NTILE/2 entries per thread) from a
+//    per-patch table of the interior X rows of every coarse cell;
+//  * M^{-1}: Gauss-Jordan sweeps on that register tile (like FullMatrix::gauss_jordan, source/LOD.cc:553); the
+//    pivot row / column travel through a double-buffered shared vector, one barrier per sweep;
+//  * BD and the Gram matrix use FP64 mma.sync tiles: warp w owns the coarse-column tile [8w, 8w+8) of BD and two
+//    tile rows (w and NTILE-1-w, lower triangle only) of G, whose accumulators stay in registers while the
+//    boundary rows stream through shared memory in tiles of 32.
+// Included by kernels.cu.
 #pragma once
 
 namespace slod {
 
-constexpr int kDTB = 32;  // boundary rows per tile
+constexpr int kDTB = 32;    // boundary rows per tile
+constexpr int kDNB = 56;    // stencil slots reserved per boundary row (27 * spacedim <= 54)
 
 template <int NTILE>
 __global__ void __launch_bounds__(32 * NTILE, 1)
@@ -16,18 +24,23 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   constexpr int NT = 32 * NTILE;
   constexpr int NC = 8 * NTILE;   // padded coarse dimension
   constexpr int LDM = NC + 4;     // LDM % 16 == 4 : conflict-free fragment loads
+  constexpr int TW = NTILE / 2;   // register tile: 4 rows x TW columns per thread, 16 column groups
   extern __shared__ double smem[];
   double *sCoef = smem;
-  double *sM = sCoef + lay.coef_doubles;  // [NC][LDM]
-  double *sT = sM + NC * LDM;             // [kDTB][LDM]
-  double *sCol = sT + kDTB * LDM;         // [NC]
-  double *sRow = sCol + NC;               // [NC]
-  double *sArow = sRow + NC;              // [kDTB][54]
-  int *sAnbr = (int *)(sArow + kDTB * 54);
-  int *sBlist = sAnbr + kDTB * 54;
+  double *sM = sCoef + lay.coef_doubles;  // [NC][LDM]   M^{-1} for the mma B operand
+  double *sT = sM + NC * LDM;             // [kDTB][LDM] W tile, then BD tile
+  double *sPivRow = sT + kDTB * LDM;      // [2][NC]
+  double *sPivCol = sPivRow + 2 * NC;     // [2][NC]
+  double *sArow = sPivCol + 2 * NC;       // [kDTB][kDNB] compact stencil values of the boundary rows
+  int *sAnbr = (int *)(sArow + kDTB * kDNB);  // [kDTB][kDNB] interior dof of each compact entry
+  int *sAcnt = sAnbr + kDTB * kDNB;           // [kDTB]
+  int *sMList = sAcnt + kDTB;                 // [NC][28] X rows of each coarse row: (xrow << 2 | log2 weight), count first
+  int *sBlist = sMList + NC * 28;             // [nb_max] boundary dofs
   __shared__ int sNb;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int r0 = 4 * ty, c0 = TW * tx;
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int pid = patch_ids[w];
@@ -37,30 +50,28 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
     load_coef(geo, d_coef, sCoef);
     if (tid == 0) sNb = 0;
-    for (int idx = tid; idx < NC * LDM; idx += NT) sM[idx] = 0.0;
-    __syncthreads();
-
-    // ---- M = P_i^T X / H^d ----
-    const int npc = cP.n + 1;
-    const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;
-    const double scale = cP.pw / cP.Hd;
-    for (int idx = tid; idx < ncd * NC; idx += NT) {
-      const int row = idx / NC, col = idx % NC;
-      if (col >= ncd) continue;
-      const int comp = row % s;
-      int k[3];
-      col_to_cell(cP, geo, row / s, k);
-      double acc = 0.0;
-      for (int l = 0; l < nloc; ++l) {
-        int tt[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
-        int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
-        if (node_class(cP, geo, a) != 0) continue;
-        double wgt = 1.0;
-        for (int x = 0; x < cP.dim; ++x)
-          if (tt[x] != 0 && tt[x] != cP.n) wgt *= 2.0;
-        acc += wgt * X[(size_t)(interior_index(geo, a) * s + comp) * lay.ldx + col];
+    // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row ----
+    {
+      const int npc = cP.n + 1;
+      const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;
+      for (int row = tid; row < NC; row += NT) {
+        int cnt = 0;
+        if (row < ncd) {
+          const int comp = row % s;
+          int k[3];
+          col_to_cell(cP, geo, row / s, k);
+          for (int l = 0; l < nloc; ++l) {
+            int tt[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
+            int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
+            if (node_class(cP, geo, a) != 0) continue;
+            int lg = 0;
+            for (int x = 0; x < cP.dim; ++x)
+              if (tt[x] != 0 && tt[x] != cP.n) ++lg;
+            if (cnt < 27) sMList[row * 28 + 1 + cnt++] = ((interior_index(geo, a) * s + comp) << 2) | lg;
+          }
+        }
+        sMList[row * 28] = cnt;
       }
-      sM[row * LDM + col] = acc * scale;
     }
     if (geo.slod && tid < 32) {  // boundary dofs, ascending
       int count = 0;
@@ -83,32 +94,99 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     }
     __syncthreads();
 
-    // ---- M^{-1}: in-place Gauss-Jordan sweeps ----
-    for (int k = 0; k < ncd; ++k) {
-      const double piv = sM[k * LDM + k];
-      for (int j = tid; j < ncd; j += NT) {
-        sCol[j] = sM[j * LDM + k];
-        sRow[j] = sM[k * LDM + j] / piv;
-      }
-      if (tid == 0 && !(piv > 0.0)) atomicOr(&status[pid], 2);
-      __syncthreads();
-      for (int idx = tid; idx < ncd * NC; idx += NT) {
-        const int i = idx / NC, j = idx % NC;
-        if (j >= ncd) continue;
-        double v;
-        if (i == k && j == k) v = 1.0 / piv;
-        else if (i == k) v = sRow[j];
-        else if (j == k) v = -sCol[i] / piv;
-        else v = sM[i * LDM + j] - sCol[i] * sRow[j];
-        sM[i * LDM + j] = v;
-      }
-      __syncthreads();
-    }
+    // ---- M = P_i^T X / H^d into the register tile (padding rows/cols: identity) ----
+    double m[4][TW];
     {
+      const double scale = cP.pw / cP.Hd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < TW; ++j) m[i][j] = 0.0;
+        const int row = r0 + i;
+        const int cnt = sMList[row * 28];
+        for (int l = 0; l < cnt; ++l) {
+          const int e = sMList[row * 28 + 1 + l];
+          const double wgt = (double)(1 << (e & 3));
+          const double *xr = X + (size_t)(e >> 2) * lay.ldx + c0;
+#pragma unroll
+          for (int j = 0; j < TW; j += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(xr + j);
+            m[i][j] += wgt * v.x;
+            m[i][j + 1] += wgt * v.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TW; ++j) {
+          m[i][j] *= scale;
+          if (row >= ncd || c0 + j >= ncd) m[i][j] = (row == c0 + j) ? 1.0 : 0.0;
+        }
+      }
+    }
+    // ---- M^{-1}: Gauss-Jordan sweeps on the register tile ----
+    {
+      int badpiv = 0;
+      for (int k = 0; k < ncd; ++k) {
+        const int kb = (k & 1) * NC;
+        if (ty == (k >> 2)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i == (k & 3)) {
+#pragma unroll
+              for (int j = 0; j < TW; ++j) sPivRow[kb + c0 + j] = m[i][j];
+            }
+        }
+        if (tx == k / TW) {
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+            if (j == k % TW) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][j];
+            }
+        }
+        __syncthreads();
+        const double piv = sPivRow[kb + k];
+        if (!(piv > 0.0)) badpiv = 1;
+        const double ipiv = 1.0 / piv;
+        double rw[TW], cl[4];
+#pragma unroll
+        for (int j = 0; j < TW; ++j) rw[j] = sPivRow[kb + c0 + j] * ipiv;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cl[i] = sPivCol[kb + r0 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
+        if (tx == k / TW) {
+#pragma unroll
+          for (int j = 0; j < TW; ++j)
+            if (j == k % TW) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) m[i][j] = -cl[i] * ipiv;
+            }
+        }
+        if (ty == (k >> 2)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i == (k & 3)) {
+#pragma unroll
+              for (int j = 0; j < TW; ++j) m[i][j] = (c0 + j == k) ? ipiv : rw[j];
+            }
+        }
+      }
+      if (badpiv && tid == 0) atomicOr(&status[pid], 2);
       double *Mo = Minv_out + (size_t)w * lay.m_stride;
-      for (int idx = tid; idx < ncd * ncd; idx += NT) Mo[idx] = sM[(idx / ncd) * LDM + idx % ncd];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) {
+          const int row = r0 + i, col = c0 + j;
+          const bool in = row < ncd && col < ncd;
+          sM[row * LDM + col] = in ? m[i][j] : 0.0;
+          if (in) Mo[row * ncd + col] = m[i][j];
+        }
     }
     if (!geo.slod) continue;
+    __syncthreads();
 
     // ---- BD tiles and Gram accumulation ----
     double gacc[NTILE + 1][2];
@@ -119,43 +197,76 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     const int per_row = nst * s;
     const int ksteps = (ncd + 3) >> 2;
     const int I1 = warp, I2 = NTILE - 1 - warp;
+    const int lgn = __ffs(cP.n) - 1;
     for (int t0 = 0; t0 < nbd; t0 += kDTB) {
       const int nt = min(kDTB, nbd - t0);
-      for (int idx = tid; idx < nt * per_row; idx += NT) {
-        const int rb = idx / per_row;
-        int e = idx % per_row;
-        const int cb = e % s;
-        e /= s;
-        int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
-        const int dof = sBlist[t0 + rb];
-        int a[3];
-        node_coords(geo, dof / s, a);
-        int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
-        bool ok = true;
-        for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
-        if (ok) {
-          sAnbr[rb * 54 + (idx % per_row)] = interior_index(geo, b) * s + cb;
-          sArow[rb * 54 + (idx % per_row)] = stiff_entry(cP, geo, sCoef, a, dl, dof % s, cb);
-        } else {
-          sAnbr[rb * 54 + (idx % per_row)] = -1;
+      // compact stencil rows: one warp per boundary row, ballot compaction keeps the slot order
+      for (int rb = warp; rb < kDTB; rb += NTILE) {
+        int count = 0;
+        if (rb < nt) {
+          const int dof = sBlist[t0 + rb];
+          int a[3];
+          node_coords(geo, dof / s, a);
+          for (int base = 0; base < per_row; base += 32) {
+            const int slot = base + lane;
+            bool ok = slot < per_row;
+            int nbr = 0;
+            double val = 0.0;
+            if (ok) {
+              const int cb = slot % s, e = slot / s;
+              int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
+              int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
+              for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
+              if (ok) {
+                nbr = interior_index(geo, b) * s + cb;
+                val = stiff_entry(cP, geo, sCoef, a, dl, dof % s, cb);
+              }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+              const int pos = count + __popc(mask & ((1u << lane) - 1u));
+              sAnbr[rb * kDNB + pos] = nbr;
+              sArow[rb * kDNB + pos] = val;
+            }
+            count += __popc(mask);
+          }
         }
+        if (lane == 0) sAcnt[rb] = count;
       }
       __syncthreads();
-      // W tile = S_b X - P_b (zero padded to 32 x NC)
+      // W tile = S_b X (zero padded to 32 x NC)
       for (int idx = tid; idx < kDTB * NC; idx += NT) {
         const int rb = idx / NC, col = idx % NC;
         double acc = 0.0;
         if (rb < nt && col < ncd) {
-          const int dof = sBlist[t0 + rb];
-          int a[3];
-          node_coords(geo, dof / s, a);
-          acc = -proj_entry(cP, geo, a, dof % s, col);
-          for (int e = 0; e < per_row; ++e) {
-            const int nb_ = sAnbr[rb * 54 + e];
-            if (nb_ >= 0) acc += sArow[rb * 54 + e] * X[(size_t)nb_ * lay.ldx + col];
-          }
+          const int cnt = sAcnt[rb];
+          for (int e = 0; e < cnt; ++e) acc += sArow[rb * kDNB + e] * X[(size_t)sAnbr[rb * kDNB + e] * lay.ldx + col];
         }
         sT[rb * LDM + col] = acc;
+      }
+      __syncthreads();
+      // ... - P_b : every boundary dof lies in at most 2^dim coarse cells
+      for (int idx = tid; idx < nt * 8; idx += NT) {
+        const int rb = idx >> 3, corner = idx & 7;
+        if (corner >= (1 << cP.dim)) continue;
+        const int dof = sBlist[t0 + rb];
+        int a[3];
+        node_coords(geo, dof / s, a);
+        int kc[3] = {0, 0, 0};
+        double wgt = cP.pw;
+        bool ok = true;
+        for (int x = 0; x < cP.dim; ++x) {
+          const int q = a[x] >> lgn, rem = a[x] - (q << lgn);
+          if ((corner >> x) & 1) {
+            if (rem != 0 || q < 1) ok = false;
+            kc[x] = q - 1;
+          } else {
+            if (q > geo.m[x] - 1) ok = false;
+            kc[x] = q;
+            if (rem != 0) wgt *= 2.0;
+          }
+        }
+        if (ok) sT[rb * LDM + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
       }
       __syncthreads();
       // BD tile = W tile * Minv : warp owns 8 columns, 4 row tiles
@@ -181,7 +292,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         for (int e = 0; e <= NTILE; ++e) {
           const bool first = (e <= I1);
           const int J = first ? e : e - (I1 + 1);
-          if (!first && J > I2) continue;
           dmma884(gacc[e][0], gacc[e][1], first ? a1 : a2, rowp[8 * J]);
         }
       }
@@ -193,7 +303,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         const bool first = (e <= I1);
         const int I = first ? I1 : I2;
         const int J = first ? e : e - (I1 + 1);
-        if (J > I) continue;
         const int i = 8 * I + g, j = 8 * J + 2 * t;
         if (i < ncd) {
           if (j < ncd) { Go[i * ncd + j] = gacc[e][0]; if (I != J) Go[j * ncd + i] = gacc[e][0]; }

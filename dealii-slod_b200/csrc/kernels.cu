@@ -961,8 +961,8 @@ static cudaError_t launch_dense_t(int grid, size_t smem, cudaStream_t st, const 
 }
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
   const int NC = 8 * ntile, LDM = NC + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 2 * NC + kDTB * 54) +
-         sizeof(int) * ((size_t)kDTB * 54 + nb_max + 8);
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 4 * NC + kDTB * kDNB) +
+         sizeof(int) * ((size_t)kDTB * kDNB + kDTB + NC * 28 + nb_max + 8);
 }
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, double *Minv, double *G, double *diag,
