@@ -65,7 +65,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
             int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
             if (node_class(cP, geo, a) != 0) continue;
             int lg = 0;
-            for (int x = 0; x < cP.dim; ++x)
+            _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim)
               if (tt[x] != 0 && tt[x] != cP.n) ++lg;
             if (cnt < 27) sMList[row * 28 + 1 + cnt++] = ((interior_index(geo, a) * s + comp) << 2) | lg;
           }
@@ -127,21 +127,27 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       int badpiv = 0;
       for (int k = 0; k < ncd; ++k) {
         const int kb = (k & 1) * NC;
+        // NB: the pivot row / column are picked with value selects on statically indexed registers; an
+        // `if (i == k & 3) ... m[i][j]` loop would be turned into a dynamically indexed (local-memory) array.
+        const int ki = k & 3, kj = k % TW;
         if (ty == (k >> 2)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i == (k & 3)) {
-#pragma unroll
-              for (int j = 0; j < TW; ++j) sPivRow[kb + c0 + j] = m[i][j];
-            }
+          for (int j = 0; j < TW; ++j) {
+            double v = m[0][j];
+            v = (ki == 1) ? m[1][j] : v;
+            v = (ki == 2) ? m[2][j] : v;
+            v = (ki == 3) ? m[3][j] : v;
+            sPivRow[kb + c0 + j] = v;
+          }
         }
         if (tx == k / TW) {
 #pragma unroll
-          for (int j = 0; j < TW; ++j)
-            if (j == k % TW) {
+          for (int i = 0; i < 4; ++i) {
+            double v = m[i][0];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][j];
-            }
+            for (int j = 1; j < TW; ++j) v = (kj == j) ? m[i][j] : v;
+            sPivCol[kb + r0 + i] = v;
+          }
         }
         __syncthreads();
         const double piv = sPivRow[kb + k];
@@ -152,24 +158,22 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         for (int j = 0; j < TW; ++j) rw[j] = sPivRow[kb + c0 + j] * ipiv;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cl[i] = sPivCol[kb + r0 + i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
-        if (tx == k / TW) {
-#pragma unroll
-          for (int j = 0; j < TW; ++j)
-            if (j == k % TW) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) m[i][j] = -cl[i] * ipiv;
-            }
-        }
-        if (ty == (k >> 2)) {
+        const bool own_row = (ty == (k >> 2)), own_col = (tx == k / TW);
+        if (!own_row && !own_col) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (i == (k & 3)) {
 #pragma unroll
-              for (int j = 0; j < TW; ++j) m[i][j] = (c0 + j == k) ? ipiv : rw[j];
+            for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+              const bool pr = own_row && (ki == i), pc = own_col && (kj == j);
+              double v = m[i][j] - cl[i] * rw[j];
+              v = pc ? -cl[i] * ipiv : v;
+              v = pr ? (pc ? ipiv : rw[j]) : v;
+              m[i][j] = v;
             }
         }
       }
@@ -216,7 +220,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
               const int cb = slot % s, e = slot / s;
               int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
               int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
-              for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
+              _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) ok = ok && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
               if (ok) {
                 nbr = interior_index(geo, b) * s + cb;
                 val = stiff_entry(cP, geo, sCoef, a, dl, dof % s, cb);
@@ -255,7 +259,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         int kc[3] = {0, 0, 0};
         double wgt = cP.pw;
         bool ok = true;
-        for (int x = 0; x < cP.dim; ++x) {
+        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) {
           const int q = a[x] >> lgn, rem = a[x] - (q << lgn);
           if ((corner >> x) & 1) {
             if (rem != 0 || q < 1) ok = false;

@@ -146,7 +146,7 @@ SLOD_HD int interior_index(const Geom &g, const int a[3]) {
 // bit1 = domain boundary (id 0); 0 = internal.  Both bits may be set.
 SLOD_HD int node_class(const Params &P, const Geom &g, const int a[3]) {
   int cls = 0;
-  for (int x = 0; x < P.dim; ++x) {
+  _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < P.dim) {
     if (a[x] == 0) cls |= g.domlo[x] ? 2 : 1;
     if (a[x] == g.p[x] - 1) cls |= g.domhi[x] ? 2 : 1;
   }
@@ -159,7 +159,7 @@ SLOD_HD double proj_entry(const Params &P, const Geom &g, const int a[3], int ca
   int k[3];
   col_to_cell(P, g, col / P.s, k);
   double wgt = P.pw;
-  for (int x = 0; x < P.dim; ++x) {
+  _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < P.dim) {
     int t = a[x] - P.n * k[x];
     if (t < 0 || t > P.n) return 0.0;
     if (t != 0 && t != P.n) wgt *= 2.0;

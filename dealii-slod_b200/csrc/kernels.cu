@@ -134,7 +134,7 @@ k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__res
         idof_to_node(g, r, a, ca);
         int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
         bool inside = true;
-        for (int x = 0; x < cP.dim; ++x) inside = inside && (b[x] >= 1 && b[x] <= g.p[x] - 2);
+        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) inside = inside && (b[x] >= 1 && b[x] <= g.p[x] - 2);
         if (!inside) continue;
         const int c = interior_index(g, b) * cP.s + cb;
         if (c > r) continue;
@@ -339,7 +339,7 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
         int a[3] = {k[0] * cP.n + t[0], k[1] * cP.n + t[1], (cP.dim == 3) ? k[2] * cP.n + t[2] : 0};
         if (node_class(cP, g, a) != 0) continue;
         double wgt = 1.0;
-        for (int x = 0; x < cP.dim; ++x)
+        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim)
           if (t[x] != 0 && t[x] != cP.n) wgt *= 2.0;
         acc += wgt * X[(size_t)(interior_index(g, a) * s + comp) * lay.ldx + col];
       }
@@ -416,7 +416,7 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
         node_coords(g, dof / s, a);
         int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
         bool ok = true;
-        for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 1 && b[x] <= g.p[x] - 2);
+        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) ok = ok && (b[x] >= 1 && b[x] <= g.p[x] - 2);
         if (ok) {
           sAnbr[idx] = interior_index(g, b) * s + cb;
           sArow[idx] = stiff_entry(cP, g, sCoef, a, dl, dof % s, cb);
@@ -828,7 +828,7 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
               int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
               int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
               bool ok = true;
-              for (int x = 0; x < cP.dim; ++x) ok = ok && (b[x] >= 0 && b[x] <= g.p[x] - 1);
+              _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) ok = ok && (b[x] >= 0 && b[x] <= g.p[x] - 1);
               if (!ok) continue;
               const int nb_ = node_index(g, b);
               for (int cb = 0; cb < s; ++cb) {
@@ -868,7 +868,7 @@ k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const d
       int qc[3] = {cen[0] + D[0], cen[1] + D[1], cen[2] + D[2]};
       double val = 0.0;
       bool valid = true;
-      for (int x = 0; x < cP.dim; ++x) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
+      _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
       if (valid) {
         const int qid = (int)morton_encode(qc, cP.dim, cP.ref);
         const Geom gq = make_geom(cP, qid);

@@ -148,7 +148,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           lower_offset(e, dl);
           int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
           bool inside = true;
-          for (int x = 0; x < cP.dim; ++x) inside = inside && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
+          _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) inside = inside && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
           for (int cb = 0; cb < sdim; ++cb) {
             const bool use = inside && (e < nlow || cb <= ca);
             sSt[(size_t)r * stw + e * sdim + cb] = use ? stiff_entry(cP, geo, sCoef, a, dl, ca, cb) : 0.0;
@@ -228,7 +228,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         if (cc < 0 || ((cc >> 15) & 1) != ca) continue;
         double wgt = cP.pw;
         bool in = true;
-        for (int x = 0; x < cP.dim; ++x) {
+        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) {
           const int tt = ((pk >> (5 * x)) & 31) - n * ((cc >> (5 * x)) & 31);
           if (tt < 0 || tt > n) in = false;
           if (tt != 0 && tt != n) wgt *= 2.0;
