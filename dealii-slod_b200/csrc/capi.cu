@@ -59,10 +59,11 @@ struct slod_ctx {
   long long mma_lws_per_cta = 0;
   SolveLayout sl{};
   DenseLayout dl{};
-  SelectLayout el{};
+  SelectPlan sp{};
+  SelectBuffers sb{};
   FinishLayout fl{};
-  size_t smem_solve = 0, smem_dense = 0, smem_select = 0, smem_finish = 0, smem_coarse = 0;
-  int grid_solve = 0, grid_dense = 0, grid_select = 0, grid_finish = 0, grid_coarse = 0;
+  size_t smem_solve = 0, smem_dense = 0, smem_finish = 0, smem_coarse = 0;
+  int grid_solve = 0, grid_dense = 0, grid_finish = 0, grid_coarse = 0;
   int bw_max = 0, nb_max = 0;
   cudaEvent_t ev[10]{};
   Timings tm;
@@ -234,6 +235,7 @@ void free_dev(slod_ctx *c) {
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
   F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
+  F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
 }
 
 // Expand the caller's tables (problem_parameter::value, include/Diffusion.h:40-53) onto the fine sub-cell
@@ -302,6 +304,28 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
   CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
   CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
+  // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
+  {
+    SelectPlan &sp = ctx->sp;
+    SelectBuffers &sb = ctx->sb;
+    const size_t items = (size_t)chunk * P.s;
+    sb.counters = ctx->d_counter;
+    CK(cudaMalloc(&sb.eig_list, sizeof(int) * items));
+    CK(cudaMalloc(&sb.jac_list, sizeof(int) * items));
+    if (sp.use_ql) {
+      const size_t per_item = sizeof(double) * ((size_t)sp.eig.h_stride + sp.eig.v_stride) +
+                              (size_t)sp.eig.log_cap * (sizeof(double2) + sizeof(unsigned short)) + 2 * sizeof(int);
+      size_t cap = std::max<size_t>(64, ((size_t)4 << 30) / per_item);
+      cap = std::min(cap, items);
+      sp.eig.cap_items = (int)cap;
+      CK(cudaMalloc(&sb.H, sizeof(double) * (size_t)sp.eig.h_stride * cap));
+      CK(cudaMalloc(&sb.V, sizeof(double) * (size_t)sp.eig.v_stride * cap));
+      CK(cudaMalloc(&sb.rot_cs, sizeof(double2) * (size_t)sp.eig.log_cap * cap));
+      CK(cudaMalloc(&sb.rot_i, sizeof(unsigned short) * (size_t)sp.eig.log_cap * cap));
+      CK(cudaMalloc(&sb.rot_n, sizeof(int) * 2 * cap));
+      sp.grid_ql = (int)std::min<size_t>((cap + 7) / 8, (size_t)ctx->n_sm * 8);
+    }
+  }
   return SLOD_OK;
 }
 
@@ -348,13 +372,15 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
       CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
     CK(cudaEventRecord(ctx->ev[2], st));
-    CK(launch_patch_select(std::min(nw, ctx->grid_select), ctx->smem_select, st, ctx->d_ids, nw, ctx->d_Minv,
-                           ctx->d_G, ctx->d_cvec, ctx->d_diag, ctx->d_status, ctx->d_counter, ctx->el));
+    int nl = 0;
+    CK(launch_select_pipeline(ctx->sp, st, ctx->d_ids, nw, ctx->d_Minv, ctx->d_G, ctx->d_cvec, ctx->d_diag,
+                              ctx->d_status, ctx->sb, &nl));
+    ctx->launches += nl;
     CK(cudaEventRecord(ctx->ev[3], st));
     CK(launch_patch_finish(std::min(nw, ctx->grid_finish), ctx->smem_finish, st, ctx->d_ids, nw, ctx->d_coef,
                            ctx->d_X, ctx->d_cvec, d_phi, d_aphi, ctx->fl));
     CK(cudaEventRecord(ctx->ev[4], st));
-    ctx->launches += 4;
+    ctx->launches += 3;
     CK(cudaEventSynchronize(ctx->ev[4]));  // ids buffer is reused by the next chunk
     for (int k = 0; k < 4; ++k) {
       float ms = 0;
@@ -630,12 +656,24 @@ int slod_create(const slod_params *par, slod_ctx **out) {
       }
     }
   }
-  SelectLayout &el = ctx->el;
-  el.threads = big ? 512 : 128;
-  el.ncd_max = P.NcdMax; el.m_stride = dl.m_stride;
-  el.fast_path = getenv("SLOD_NO_FAST_SELECT") ? 0 : 1;
-  ctx->smem_select = sizeof(double) * ((size_t)P.NcdMax * (P.NcdMax + 1) / 2 + (size_t)P.NcdMax * P.NcdMax +
-                                       6 * (size_t)P.NcdMax) + sizeof(int) * (3 * (size_t)P.NcdMax + 8);
+  SelectPlan &sp = ctx->sp;
+  sp.s = P.s;
+  sp.lay.threads = big ? 512 : 128;
+  sp.lay.ncd_max = P.NcdMax; sp.lay.m_stride = dl.m_stride;
+  sp.lay.fast_path = getenv("SLOD_NO_FAST_SELECT") ? 0 : 1;
+  sp.smem_fast = select_fast_smem(P.NcdMax);
+  sp.smem_jac = select_jacobi_smem(P.NcdMax);
+  sp.eig.nmax = P.NcdMax; sp.eig.ldh = P.NcdMax;
+  sp.eig.h_stride = (long long)P.NcdMax * P.NcdMax;
+  sp.eig.v_stride = 6LL * P.NcdMax;
+  sp.eig.log_cap = std::max<long long>(3LL * P.NcdMax * P.NcdMax, 1024);
+  sp.eig.ncd_max = P.NcdMax; sp.eig.m_stride = dl.m_stride;
+  sp.eig.cap_items = 0;
+  sp.smem_tri = eig_tridiag_smem(P.NcdMax);
+  sp.smem_ql = eig_ql_smem(P.NcdMax);
+  sp.smem_fin = eig_finish_smem(P.NcdMax);
+  // the tridiagonalisation keeps columns of up to 256 rows in registers and the whole matrix in shared memory
+  sp.use_ql = (P.NcdMax - 1 <= 256 && sp.smem_tri <= prop.sharedMemPerBlockOptin && !getenv("SLOD_FORCE_JACOBI")) ? 1 : 0;
   FinishLayout &fl = ctx->fl;
   fl.coef_doubles = coef_doubles; fl.nf_max = P.NfMax; fl.ncd_max = P.NcdMax; fl.ldx = sl.ldx; fl.x_stride = sl.x_stride;
   ctx->smem_finish = sizeof(double) * ((size_t)coef_doubles + P.NfMax + P.NcdMax);
@@ -643,7 +681,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
   if ((size_t)P.NcdMax * P.NcdMax > (size_t)32 * dl.threads)
     { delete ctx; return bad(SLOD_ERR_UNSUPPORTED, "patch too large: coarse dofs per patch exceed the Gram register tile"); }
-  if (ctx->smem_solve > smem_cap || ctx->smem_dense > smem_cap || ctx->smem_select > smem_cap ||
+  if (ctx->smem_solve > smem_cap || ctx->smem_dense > smem_cap || sp.smem_fast > smem_cap || sp.smem_jac > smem_cap ||
       ctx->smem_finish > smem_cap || ctx->smem_coarse > smem_cap) {
     delete ctx;
     return bad(SLOD_ERR_UNSUPPORTED, "patch too large for the shared-memory resident solver (oversampling/subdivisions)");
@@ -655,7 +693,11 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   };
   ctx->grid_solve = ctx->n_sm * per_sm(ctx->smem_solve, sl.threads);
   ctx->grid_dense = ctx->n_sm * per_sm(ctx->smem_dense, dl.threads);
-  ctx->grid_select = ctx->n_sm * per_sm(ctx->smem_select, el.threads);
+  sp.grid_fast = ctx->n_sm * per_sm(sp.smem_fast, sp.lay.threads);
+  sp.grid_jac = ctx->n_sm * per_sm(sp.smem_jac, sp.lay.threads);
+  sp.grid_tri = ctx->n_sm * per_sm(sp.smem_tri, 256);
+  sp.grid_fin = ctx->n_sm * per_sm(sp.smem_fin, 128);
+  sp.grid_ql = ctx->n_sm * 8;
   ctx->grid_finish = ctx->n_sm * per_sm(ctx->smem_finish, 256);
   ctx->grid_coarse = ctx->n_sm * per_sm(ctx->smem_coarse, 256);
 

@@ -473,293 +473,9 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
 #include "dense_mma.cuh"
 namespace slod {
 
-// ------------------------------------------------------------------------------------------------
-// k_patch_select : thresholded pseudo-inverse through a cyclic Jacobi eigen-solver
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-
-__global__ void __launch_bounds__(512, 1)
-k_patch_select(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ Minv_in,
-               const double *__restrict__ G_in, double *__restrict__ cvec, double *__restrict__ diag,
-               int *__restrict__ status, int *__restrict__ work_counter, SelectLayout lay) {
-  extern __shared__ double smem[];
-  const int nmax = lay.ncd_max;       // >= n + 1
-  double *sG = smem;                                   // packed lower, n(n+1)/2
-  double *sV = sG + (size_t)nmax * (nmax + 1) / 2;     // [n][n]
-  double *sg = sV + (size_t)nmax * nmax;               // g
-  double *sgh = sg + nmax;                             // V^T g
-  double *sd = sgh + nmax;                             // d
-  double *slam = sd + nmax;                            // eigenvalues
-  double *sc = slam + nmax;                            // rotation cos per pair
-  double *ss = sc + nmax;                              // rotation sin per pair
-  int *sp = (int *)(ss + nmax);                        // pair p
-  int *sq = sp + nmax;                                 // pair q
-  int *sord = sq + nmax;                               // eigenvalue order (descending |lambda|)
-  __shared__ double sRed[32];
-  __shared__ double sOff;
-  __shared__ int sFlag;
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
-
-  __shared__ int sWork;
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) sWork = atomicAdd(work_counter, 1);
-    __syncthreads();
-    const int w = sWork;
-    if (w >= n_work) break;
-    const int pid = patch_ids[w];
-    const Geom g = make_geom(cP, pid);
-    const int ncd = g.Ncd, s = cP.s;
-    const double *Minv = Minv_in + (size_t)w * lay.m_stride;
-    const double *Gf = G_in + (size_t)w * lay.m_stride;
-    for (int d = 0; d < s; ++d) {
-      double *cv = cvec + ((size_t)w * s + d) * lay.ncd_max;
-      double *dg = diag + ((size_t)pid * s + d) * 8;
-      __syncthreads();
-      if (!g.slod) {  // LOD branch: c = M^{-1} e_d (source/LOD.cc:570-593)
-        for (int i = tid; i < ncd; i += NT) cv[i] = Minv[i * ncd + d];
-        if (tid == 0) { dg[0] = 0; dg[1] = 0; dg[2] = 0; dg[3] = 0; dg[5] = 0; dg[6] = 0; }
-        continue;
-      }
-      const int n = ncd - 1;               // considered_candidates
-      // ---- fast path: if no singular value is thresholded and the truncation loop does not fire, the
-      // reference's d = -G^+ g (source/LOD.cc:667-671) is the solution of the SPD system G d = -g: Cholesky in
-      // shared memory.  Any doubt (tiny pivot, ||d||_inf close to or above 0.5) goes to the eigen-solver. ----
-      if (lay.fast_path) {
-        double *Lc = sV;  // [n][n] full storage, lower part used
-        for (int idx = tid; idx < n * n; idx += NT) {
-          const int i = idx / n, j = idx % n;
-          Lc[idx] = (j <= i) ? Gf[(i + (i >= d)) * ncd + (j + (j >= d))] : 0.0;
-        }
-        for (int i = tid; i < n; i += NT) { sg[i] = Gf[(i + (i >= d)) * ncd + d]; sd[i] = -sg[i]; }
-        if (tid == 0) sFlag = 0;
-        __syncthreads();
-        double dmax = 0.0, pmin = 1e300;
-        for (int i = 0; i < n; ++i) dmax = fmax(dmax, Lc[i * n + i]);
-        for (int k = 0; k < n; ++k) {
-          __syncthreads();
-          const double akk = Lc[k * n + k];   // stays untouched during this step; sqrt kept in slam[k]
-          pmin = fmin(pmin, akk);
-          const double inv = 1.0 / sqrt(akk);
-          for (int i = k + 1 + tid; i < n; i += NT) Lc[i * n + k] *= inv;
-          if (tid == 0) slam[k] = akk * inv;
-          __syncthreads();
-          const int m = n - k - 1;
-          for (int idx = tid; idx < m * m; idx += NT) {
-            const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-            if (j <= i) Lc[i * n + j] -= Lc[i * n + k] * Lc[j * n + k];
-          }
-        }
-        __syncthreads();
-        const bool spd_ok = (pmin > 1e-12 * dmax);
-        if (spd_ok && warp == 0) {
-          // L z = -g, then L^T x = z ; one warp, column-oriented updates
-          for (int k = 0; k < n; ++k) {
-            const double zk = sd[k] / slam[k];
-            __syncwarp();
-            if (lane == 0) sd[k] = zk;
-            for (int i = k + 1 + lane; i < n; i += 32) sd[i] -= Lc[i * n + k] * zk;
-            __syncwarp();
-          }
-          for (int k = n - 1; k >= 0; --k) {
-            const double xk = sd[k] / slam[k];
-            __syncwarp();
-            if (lane == 0) sd[k] = xk;
-            for (int j = lane; j < k; j += 32) sd[j] -= Lc[k * n + j] * xk;
-            __syncwarp();
-          }
-          double m = 0.0;
-          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sd[r]));
-          m = warp_max(m);
-          if (lane == 0) {
-            if (m < 0.49) {
-              sFlag = 1;
-              dg[0] = m; dg[1] = 0; dg[2] = dmax; dg[3] = pmin; dg[5] = 1; dg[6] = 0;
-            }
-          }
-        }
-        __syncthreads();
-        if (sFlag) {
-          for (int i = tid; i < ncd; i += NT) {
-            double acc = Minv[i * ncd + d];
-            for (int k = 0; k < n; ++k) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
-            cv[i] = acc;
-          }
-          continue;
-        }
-      }
-      const int np = (n + 1) & ~1;         // even player count for the tournament
-      const int half = np / 2;
-      // other_phi: all coarse dofs but d  (source/LOD.cc:637-640)
-      for (int idx = tid; idx < n * n; idx += NT) {
-        const int i = idx / n, j = idx % n;
-        if (j <= i) sG[i * (i + 1) / 2 + j] = Gf[(i + (i >= d)) * ncd + (j + (j >= d))];
-        sV[idx] = (i == j) ? 1.0 : 0.0;
-      }
-      for (int i = tid; i < n; i += NT) sg[i] = Gf[(i + (i >= d)) * ncd + d];
-      __syncthreads();
-      double maxdiag = 0.0;
-      for (int i = 0; i < n; ++i) maxdiag = fmax(maxdiag, fabs(sG[i * (i + 1) / 2 + i]));
-      const double tol = 1e-17 * maxdiag;
-      int sweeps = 0;
-      for (; sweeps < 40; ++sweeps) {
-        if (tid == 0) sOff = 0.0;
-        __syncthreads();
-        double myoff = 0.0;
-        for (int step = 0; step < np - 1; ++step) {
-          // rotation parameters for the `half` disjoint pairs of this step
-          if (tid < half) {
-            int a, b;
-            if (tid == 0) { a = step; b = np - 1; }
-            else { a = (step + tid) % (np - 1); b = (step - tid + (np - 1)) % (np - 1); }
-            int p = min(a, b), q = max(a, b);
-            double c = 1.0, sn = 0.0;
-            if (q < n) {
-              const double apq = sG[q * (q + 1) / 2 + p];
-              myoff = fmax(myoff, fabs(apq));
-              if (fabs(apq) > tol) {
-                const double app = sG[p * (p + 1) / 2 + p], aqq = sG[q * (q + 1) / 2 + q];
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                c = 1.0 / sqrt(1.0 + t * t);
-                sn = t * c;
-              }
-            } else {
-              q = -1;  // dummy player: no rotation, but p's row still needs no update
-            }
-            sp[tid] = p; sq[tid] = q; sc[tid] = c; ss[tid] = sn;
-          }
-          __syncthreads();
-          // G <- J^T G J in 2x2 blocks (pair k1 rows, pair k2 columns), lower block triangle only
-          for (int idx = tid; idx < half * half; idx += NT) {
-            const int k1 = idx / half, k2 = idx % half;
-            if (k2 > k1) continue;
-            const int p1 = sp[k1], q1 = sq[k1], p2 = sp[k2], q2 = sq[k2];
-            const double c1 = sc[k1], s1 = ss[k1], c2 = sc[k2], s2 = ss[k2];
-            if (q1 < 0 && q2 < 0) continue;
-            if (k1 == k2) {
-              if (q1 < 0) continue;
-              const double app = sG[sym_idx(p1, p1)], aqq = sG[sym_idx(q1, q1)], apq = sG[sym_idx(q1, p1)];
-              // [c -s; s c]^T ... : new diagonal from the full similarity transform
-              const double npp = c1 * c1 * app - 2.0 * c1 * s1 * apq + s1 * s1 * aqq;
-              const double nqq = s1 * s1 * app + 2.0 * c1 * s1 * apq + c1 * c1 * aqq;
-              const double npq = (c1 * c1 - s1 * s1) * apq + c1 * s1 * (app - aqq);
-              sG[sym_idx(p1, p1)] = npp;
-              sG[sym_idx(q1, q1)] = nqq;
-              sG[sym_idx(q1, p1)] = (s1 != 0.0) ? 0.0 : npq;
-              continue;
-            }
-            // rows {p1,q1} (q1 may be absent), cols {p2,q2} (q2 may be absent)
-            double b00 = sG[sym_idx(p1, p2)];
-            double b01 = (q2 >= 0) ? sG[sym_idx(p1, q2)] : 0.0;
-            double b10 = (q1 >= 0) ? sG[sym_idx(q1, p2)] : 0.0;
-            double b11 = (q1 >= 0 && q2 >= 0) ? sG[sym_idx(q1, q2)] : 0.0;
-            const double t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
-            const double t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
-            b00 = c2 * t00 - s2 * t01; b01 = s2 * t00 + c2 * t01;
-            b10 = c2 * t10 - s2 * t11; b11 = s2 * t10 + c2 * t11;
-            sG[sym_idx(p1, p2)] = b00;
-            if (q2 >= 0) sG[sym_idx(p1, q2)] = b01;
-            if (q1 >= 0) sG[sym_idx(q1, p2)] = b10;
-            if (q1 >= 0 && q2 >= 0) sG[sym_idx(q1, q2)] = b11;
-          }
-          // V <- V J
-          for (int idx = tid; idx < n * half; idx += NT) {
-            const int r = idx / half, k = idx % half;
-            const int q = sq[k];
-            if (q < 0) continue;
-            const int p = sp[k];
-            const double c = sc[k], sn = ss[k];
-            const double vp = sV[r * n + p], vq = sV[r * n + q];
-            sV[r * n + p] = c * vp - sn * vq;
-            sV[r * n + q] = sn * vp + c * vq;
-          }
-          __syncthreads();
-        }
-        // converged when no off-diagonal entry seen in this sweep exceeded tol
-        myoff = warp_max(myoff);
-        if (lane == 0) sRed[warp] = myoff;
-        __syncthreads();
-        if (tid == 0) {
-          double m = 0.0;
-          for (int i = 0; i < nwarp; ++i) m = fmax(m, sRed[i]);
-          sOff = m;
-        }
-        __syncthreads();
-        if (sOff <= tol) { ++sweeps; break; }
-      }
-      // eigenvalues, order by descending |lambda| (LAPACK singular value order), ghat = V^T g
-      for (int i = tid; i < n; i += NT) {
-        slam[i] = sG[i * (i + 1) / 2 + i];
-        sord[i] = i;  // stays a valid permutation even if NaNs break the ranking below
-      }
-      __syncthreads();
-      for (int i = tid; i < n; i += NT) {
-        const double li = fabs(slam[i]);
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-          const double lj = fabs(slam[j]);
-          rank += (lj > li) || (lj == li && j < i);
-        }
-        if (li == li) sord[rank] = i;
-        double acc = 0.0;
-        for (int r = 0; r < n; ++r) acc += sV[r * n + i] * sg[r];
-        sgh[i] = acc;
-      }
-      __syncthreads();
-      const double sig0 = fabs(slam[sord[0]]);
-      // d = - sum_k v_k w_k ghat_k, w_k = 1/lambda_k if |lambda_k| > 1e-15 sigma_0 (source/LOD.cc:667-671)
-      for (int r = tid; r < n; r += NT) {
-        double acc = 0.0;
-        for (int k = 0; k < n; ++k) {
-          const double lk = slam[k];
-          if (fabs(lk) > 1e-15 * sig0) acc += sV[r * n + k] * (sgh[k] / lk);
-        }
-        sd[r] = -acc;
-      }
-      __syncthreads();
-      // truncation loop (source/LOD.cc:703-725), one warp
-      if (warp == 0) {
-        int steps = 0;
-        double dinf0 = -1.0, kept = fabs(slam[sord[n - 1]]);
-        int i = n - 1;
-        for (; i >= 0; --i) {
-          double m = 0.0;
-          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sd[r]));
-          m = warp_max(m);
-          if (dinf0 < 0.0) dinf0 = m;
-          if (m < 0.5) break;
-          const int k = sord[i];
-          const double lk = slam[k];
-          if (fabs(lk) > 1e-15 * sig0) {
-            const double f = sgh[k] / lk;
-            for (int r = lane; r < n; r += 32) sd[r] += sV[r * n + k] * f;
-          }
-          __syncwarp();
-          ++steps;
-        }
-        // smallest singular value still in use
-        {
-          int last = n - 1 - steps;
-          if (last < 0) last = 0;
-          while (last > 0 && !(fabs(slam[sord[last]]) > 1e-15 * sig0)) --last;
-          kept = fabs(slam[sord[last]]);
-        }
-        if (lane == 0) {
-          dg[0] = dinf0; dg[1] = steps; dg[2] = sig0; dg[3] = kept; dg[5] = 2; dg[6] = sweeps;
-          if (sweeps >= 40) atomicOr(&status[pid], 4);
-        }
-      }
-      __syncthreads();
-      // c = M^{-1} (e_d + sum_k d_k e_other[k])  (source/LOD.cc:727-743)
-      for (int i = tid; i < ncd; i += NT) {
-        double acc = Minv[i * ncd + d];
-        for (int k = 0; k < n; ++k) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
-        cv[i] = acc;
-      }
-    }
-  }
-}
+}  // namespace slod
+#include "select.cuh"
+namespace slod {
 
 // ------------------------------------------------------------------------------------------------
 // k_patch_finish : phi = X c (zero on every boundary dof), normalise, A phi
@@ -975,14 +691,47 @@ cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
-                                const double *G, double *cvec, double *diag, int *status, int *work_counter,
-                                const SelectLayout &lay) {
-  cudaError_t e = cudaFuncSetAttribute(k_patch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return e;
-  k_patch_select<<<grid, lay.threads, smem, st>>>(ids, n_work, Minv, G, cvec, diag, status, work_counter, lay);
+size_t select_fast_smem(int ncd_max) { return sizeof(double) * ((size_t)ncd_max * ncd_max + 4 * (size_t)ncd_max); }
+size_t select_jacobi_smem(int ncd_max) {
+  return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + (size_t)ncd_max * ncd_max + 6 * (size_t)ncd_max) +
+         sizeof(int) * (3 * (size_t)ncd_max + 8);
+}
+size_t eig_tridiag_smem(int nmax) { return sizeof(double) * ((size_t)nmax * (nmax | 1) + 11 * (size_t)nmax); }
+size_t eig_ql_smem(int nmax) { return sizeof(double) * 8 * 3 * (size_t)nmax; }
+size_t eig_finish_smem(int nmax) {
+  return sizeof(double) * ((size_t)nmax * kEigLd + 5 * (size_t)nmax) + sizeof(int) * ((size_t)nmax + 8);
+}
+
+cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const int *ids, int n_work, const double *Minv,
+                                   const double *G, double *cvec, double *diag, int *status, const SelectBuffers &b,
+                                   int *n_launches) {
+  cudaError_t e;
+#define SLOD_ATTR(k, sm)                                                                        \
+  if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm))) != cudaSuccess) return e
+  SLOD_ATTR(k_select_fast, pl.smem_fast);
+  SLOD_ATTR(k_select_jacobi, pl.smem_jac);
+  if ((e = cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
+  k_select_fast<<<min(n_work, pl.grid_fast), pl.lay.threads, pl.smem_fast, st>>>(
+      ids, n_work, Minv, G, cvec, diag, b.counters, pl.use_ql ? b.eig_list : b.jac_list, pl.use_ql ? 1 : 2, pl.lay);
+  ++*n_launches;
+  if (pl.use_ql) {
+    SLOD_ATTR(k_eig_tridiag, pl.smem_tri);
+    SLOD_ATTR(k_eig_ql, pl.smem_ql);
+    SLOD_ATTR(k_eig_finish, pl.smem_fin);
+    const long long items_max = (long long)n_work * pl.s;
+    for (long long off = 0; off < items_max; off += pl.eig.cap_items) {
+      k_eig_tridiag<<<pl.grid_tri, 256, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
+      k_eig_ql<<<pl.grid_ql, 256, pl.smem_ql, st>>>(ids, b.counters, b.eig_list, (int)off, b.V, b.rot_cs, b.rot_i,
+                                                   b.rot_n, pl.eig);
+      k_eig_finish<<<pl.grid_fin, 128, pl.smem_fin, st>>>(ids, b.counters, b.eig_list, (int)off, Minv, b.H, b.V,
+                                                         b.rot_cs, b.rot_i, b.rot_n, cvec, diag, b.jac_list, pl.eig);
+      *n_launches += 3;
+    }
+  }
+  k_select_jacobi<<<pl.grid_jac, pl.lay.threads, pl.smem_jac, st>>>(ids, b.counters, b.jac_list, Minv, G, cvec, diag,
+                                                                    status, pl.lay);
+  ++*n_launches;
+#undef SLOD_ATTR
   return cudaGetLastError();
 }
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,

@@ -57,9 +57,39 @@ size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max);
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, double *Minv, double *G, double *diag,
                                    int *status, const DenseLayout &lay);
-cudaError_t launch_patch_select(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Minv,
-                                const double *G, double *cvec, double *diag, int *status, int *work_counter,
-                                const SelectLayout &lay);
+// selection pipeline (select.cuh): fast path -> tridiagonalisation + QL (rotation log) -> Jacobi fallback
+struct EigLayout {
+  int nmax, ldh;
+  long long h_stride, v_stride;
+  long long log_cap;   // rotations per item
+  int ncd_max;
+  long long m_stride;
+  int cap_items;       // items per round
+};
+struct SelectPlan {
+  SelectLayout lay;
+  EigLayout eig;
+  int s;        // spacedim: items per patch
+  int use_ql;   // 0: everything that fails the fast path goes to the Jacobi kernel
+  int grid_fast, grid_tri, grid_ql, grid_fin, grid_jac;
+  size_t smem_fast, smem_tri, smem_ql, smem_fin, smem_jac;
+};
+struct SelectBuffers {
+  int *counters;   // [4]: fast-path work counter | eigen items | Jacobi items
+  int *eig_list, *jac_list;
+  double *H, *V;
+  double2 *rot_cs;
+  unsigned short *rot_i;
+  int *rot_n;
+};
+size_t select_fast_smem(int ncd_max);
+size_t select_jacobi_smem(int ncd_max);
+size_t eig_tridiag_smem(int nmax);
+size_t eig_ql_smem(int nmax);
+size_t eig_finish_smem(int nmax);
+cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const int *ids, int n_work, const double *Minv,
+                                   const double *G, double *cvec, double *diag, int *status, const SelectBuffers &b,
+                                   int *n_launches);
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                 const double *X, const double *cvec, double *phi, double *aphi,
                                 const FinishLayout &lay);
