@@ -1,0 +1,101 @@
+"""C++ host mirror of the reference driver (dealii-slod_b200/host): builds against the C ABI, speaks the reference's
+.prm dialect, fails loudly without a GPU (CPU tests) and reproduces the oracle's coarse matrix (GPU test)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "dealii-slod_b200", "host")
+
+PRM = """subsection Problem
+  set Output directory = .
+  set Output name = t
+  set Oversampling = {ell}
+  set Number of subdivisions = 2
+  set Number of global refinements = {ref}
+  set Stabilize phi_LOD candidates = true   # SLOD
+  subsection Coefficients
+    set Constant problem coefficients = false
+    set Refinement for random coefficients = {r}
+    set Random seed = {seed}
+  end
+end
+"""
+
+
+@pytest.fixture(scope="module")
+def apps():
+    res = subprocess.run(["make", "-C", HOST], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    return {n: os.path.join(HOST, n) for n in ("main_Diffusion", "main_Elasticity", "main_Diffusion3D")}
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_template_prm_and_no_cpu_fallback(apps, tmp_path):
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    res = subprocess.run([apps["main_Diffusion"]], cwd=tmp_path, capture_output=True, text=True)
+    # like the reference: exception -> message -> exit code 1 (app/main_Diffusion.cc:23-47)
+    assert res.returncode == 1
+    assert "Exception on processing" in res.stderr and "no CPU fallback" in res.stderr
+    assert "Running LOD Diffusion problem in 2D" in res.stdout
+    prm = (tmp_path / "parameters.prm").read_text()   # ParameterAcceptor writes a template when the file is missing
+    for key in ("Output directory", "Output name", "Oversampling", "Number of subdivisions",
+                "Number of global refinements", "Compare with fine global solution", "Stabilize phi_LOD candidates",
+                "Constant problem coefficients"):
+        assert f"set {key} = " in prm                   # include/LOD.h:133-143
+    assert "subsection Problem" in prm and "subsection Coefficients" in prm
+    used = (tmp_path / "used_parameters_2.prm").read_text()   # source/LOD.cc:60-62
+    assert "set Oversampling = 1" in used
+
+
+def test_prm_errors(apps, tmp_path):
+    (tmp_path / "bad.prm").write_text("subsection Problem\n  set No such key = 1\nend\n")
+    res = subprocess.run([apps["main_Elasticity"], "bad.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 1 and "no such parameter" in res.stderr
+    (tmp_path / "bad2.prm").write_text("subsection Problem\n  set Oversampling = two\nend\n")
+    res = subprocess.run([apps["main_Diffusion3D"], "bad2.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 1 and "not an integer" in res.stderr
+    (tmp_path / "bad3.prm").write_text("subsection Problem\n  set Oversampling = 1\n")
+    res = subprocess.run([apps["main_Diffusion"], "bad3.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 1 and "unterminated subsection" in res.stderr
+
+
+def _read_matrix(path):
+    raw = open(path, "rb").read()
+    n_rows, nnz = np.frombuffer(raw[:16], dtype=np.int64)
+    off = 16
+    rowptr = np.frombuffer(raw, dtype=np.int64, count=n_rows + 1, offset=off)
+    off += 8 * (n_rows + 1)
+    col = np.frombuffer(raw, dtype=np.int64, count=nnz, offset=off)
+    off += 8 * nnz
+    val = np.frombuffer(raw, dtype=np.float64, count=nnz, offset=off)
+    return rowptr, col, val
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("app,dim,s,ref,ell,r", [("main_Diffusion", 2, 1, 3, 1, 4), ("main_Elasticity", 2, 2, 3, 1, 4),
+                                                 ("main_Diffusion3D", 3, 1, 2, 1, 3)])
+def test_apps_match_oracle(apps, tmp_path, app, dim, s, ref, ell, r):
+    from oracle.slod_oracle import CoefficientTable, GlibcRand, SlodOracle, SlodProblem, reference_random_table
+    seed = 5
+    (tmp_path / "p.prm").write_text(PRM.format(ell=ell, ref=ref, r=r, seed=seed))
+    res = subprocess.run([apps[app], "p.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert f"Number of patches = {(2 ** ref) ** dim}" in res.stdout
+    rowptr, col, val = _read_matrix(tmp_path / "t_coarse_matrix.bin")
+    rng = GlibcRand(seed)                       # srand(seed); the host draws Lambda then Mu like the reference
+    tabs = [reference_random_table(dim, 1, 100, r, rng) for _ in range(s)]
+    orc = SlodOracle(SlodProblem(dim=dim, spacedim=s, n_global_refinements=ref, n_subdivisions=2, oversampling=ell,
+                                 stabilize=True, problem="diffusion" if s == 1 else "elasticity",
+                                 coefficients=[CoefficientTable(dim, r, t) for t in tabs]))
+    orc.compute_basis()
+    K, _, _ = orc.assemble_global_matrix()
+    assert np.array_equal(rowptr, K.indptr) and np.array_equal(col, K.indices)
+    assert np.abs(val - K.data).max() <= 1e-8 * np.abs(K.data).max()
