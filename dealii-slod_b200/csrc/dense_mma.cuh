@@ -24,7 +24,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   constexpr int NT = 32 * NTILE;
   constexpr int NC = 8 * NTILE;   // padded coarse dimension
   constexpr int LDM = NC + 4;     // LDM % 16 == 4 : conflict-free fragment loads
-  constexpr int TW = NTILE / 2;   // register tile: 4 rows x TW columns per thread, 16 column groups
+  constexpr int TW = NTILE / 2;   // register tile: 4 rows x TW columns per thread; thread tx owns columns tx + 16 j
+                                  // (interleaved: the pivot-row reads of a half warp are 16 consecutive doubles)
   extern __shared__ double smem[];
   double *sCoef = smem;
   double *sM = sCoef + lay.coef_doubles;  // [NC][LDM]   M^{-1} for the mma B operand
@@ -40,7 +41,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ty = tid >> 4, tx = tid & 15;
-  const int r0 = 4 * ty, c0 = TW * tx;
+  const int r0 = 4 * ty;
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int pid = patch_ids[w];
@@ -48,6 +49,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     const int ncd = geo.Ncd, s = cP.s;
     const double *X = Xbuf + (size_t)w * lay.x_stride;
     __syncthreads();
+    PH_DECL
     load_coef(geo, d_coef, sCoef);
     if (tid == 0) sNb = 0;
     // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row ----
@@ -94,6 +96,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     }
     __syncthreads();
 
+    PH(0)
     // ---- M = P_i^T X / H^d into the register tile (padding rows/cols: identity) ----
     double m[4][TW];
     {
@@ -107,46 +110,49 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         for (int l = 0; l < cnt; ++l) {
           const int e = sMList[row * 28 + 1 + l];
           const double wgt = (double)(1 << (e & 3));
-          const double *xr = X + (size_t)(e >> 2) * lay.ldx + c0;
+          const double *xr = X + (size_t)(e >> 2) * lay.ldx + tx;
 #pragma unroll
-          for (int j = 0; j < TW; j += 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(xr + j);
-            m[i][j] += wgt * v.x;
-            m[i][j + 1] += wgt * v.y;
-          }
+          for (int j = 0; j < TW; ++j) m[i][j] += wgt * xr[16 * j];
         }
 #pragma unroll
         for (int j = 0; j < TW; ++j) {
           m[i][j] *= scale;
-          if (row >= ncd || c0 + j >= ncd) m[i][j] = (row == c0 + j) ? 1.0 : 0.0;
+          if (row >= ncd || tx + 16 * j >= ncd) m[i][j] = (row == tx + 16 * j) ? 1.0 : 0.0;
         }
       }
     }
+    PH(1)
     // ---- M^{-1}: Gauss-Jordan sweeps on the register tile ----
     {
       int badpiv = 0;
+      // One sweep = one uniform rank-1 update  m_ij <- a_ij - cl_i * rw_j  with a = m outside the pivot row/column
+      // and 0 on them, cl_k = -1, rw_k = 1/piv: this yields rw_j on the pivot row, -cl_i/piv on the pivot column and
+      // 1/piv at (k,k) without any per-entry case distinction.  The owner threads pick / clear their pivot row and
+      // column registers through warp-uniform switches (static register indices, no local memory, no selects).
+#define SLOD_ROW_CASE(I, BODY) case I: { constexpr int RI = I; BODY } break;
+#define SLOD_COL_CASE(J, BODY) case J: if (J < TW) { constexpr int CJ = (J < TW) ? J : 0; BODY } break;
       for (int k = 0; k < ncd; ++k) {
         const int kb = (k & 1) * NC;
-        // NB: the pivot row / column are picked with value selects on statically indexed registers; an
-        // `if (i == k & 3) ... m[i][j]` loop would be turned into a dynamically indexed (local-memory) array.
-        const int ki = k & 3, kj = k % TW;
-        if (ty == (k >> 2)) {
-#pragma unroll
-          for (int j = 0; j < TW; ++j) {
-            double v = m[0][j];
-            v = (ki == 1) ? m[1][j] : v;
-            v = (ki == 2) ? m[2][j] : v;
-            v = (ki == 3) ? m[3][j] : v;
-            sPivRow[kb + c0 + j] = v;
+        const int ki = k & 3, kj = k >> 4;
+        const bool own_row = (ty == (k >> 2)), own_col = (tx == (k & 15));
+        if (own_row) {
+          switch (ki) {
+            SLOD_ROW_CASE(0, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
+            SLOD_ROW_CASE(1, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
+            SLOD_ROW_CASE(2, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
+            SLOD_ROW_CASE(3, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
           }
         }
-        if (tx == k / TW) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            double v = m[i][0];
-#pragma unroll
-            for (int j = 1; j < TW; ++j) v = (kj == j) ? m[i][j] : v;
-            sPivCol[kb + r0 + i] = v;
+        if (own_col) {
+          switch (kj) {
+            SLOD_COL_CASE(0, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(1, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(2, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(3, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(4, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(5, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(6, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
+            SLOD_COL_CASE(7, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
           }
         }
         __syncthreads();
@@ -155,40 +161,49 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         const double ipiv = 1.0 / piv;
         double rw[TW], cl[4];
 #pragma unroll
-        for (int j = 0; j < TW; ++j) rw[j] = sPivRow[kb + c0 + j] * ipiv;
+        for (int j = 0; j < TW; ++j) rw[j] = sPivRow[kb + tx + 16 * j] * ipiv;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cl[i] = sPivCol[kb + r0 + i];
-        const bool own_row = (ty == (k >> 2)), own_col = (tx == k / TW);
-        if (!own_row && !own_col) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < TW; ++j) {
-              const bool pr = own_row && (ki == i), pc = own_col && (kj == j);
-              double v = m[i][j] - cl[i] * rw[j];
-              v = pc ? -cl[i] * ipiv : v;
-              v = pr ? (pc ? ipiv : rw[j]) : v;
-              m[i][j] = v;
-            }
+        if (own_row) {
+          switch (ki) {
+            SLOD_ROW_CASE(0, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
+            SLOD_ROW_CASE(1, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
+            SLOD_ROW_CASE(2, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
+            SLOD_ROW_CASE(3, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
+          }
         }
+        if (own_col) {
+          switch (kj) {
+            SLOD_COL_CASE(0, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(1, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(2, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(3, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(4, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(5, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(6, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+            SLOD_COL_CASE(7, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
       }
+#undef SLOD_ROW_CASE
+#undef SLOD_COL_CASE
       if (badpiv && tid == 0) atomicOr(&status[pid], 2);
       double *Mo = Minv_out + (size_t)w * lay.m_stride;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < TW; ++j) {
-          const int row = r0 + i, col = c0 + j;
+          const int row = r0 + i, col = tx + 16 * j;
           const bool in = row < ncd && col < ncd;
           sM[row * LDM + col] = in ? m[i][j] : 0.0;
           if (in) Mo[row * ncd + col] = m[i][j];
         }
     }
+    PH(2)
     if (!geo.slod) continue;
     __syncthreads();
 
@@ -238,17 +253,20 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         if (lane == 0) sAcnt[rb] = count;
       }
       __syncthreads();
+      PH(3)
       // W tile = S_b X (zero padded to 32 x NC)
       for (int idx = tid; idx < kDTB * NC; idx += NT) {
         const int rb = idx / NC, col = idx % NC;
         double acc = 0.0;
         if (rb < nt && col < ncd) {
           const int cnt = sAcnt[rb];
+#pragma unroll 8
           for (int e = 0; e < cnt; ++e) acc += sArow[rb * kDNB + e] * X[(size_t)sAnbr[rb * kDNB + e] * lay.ldx + col];
         }
         sT[rb * LDM + col] = acc;
       }
       __syncthreads();
+      PH(4)
       // ... - P_b : every boundary dof lies in at most 2^dim coarse cells
       for (int idx = tid; idx < nt * 8; idx += NT) {
         const int rb = idx >> 3, corner = idx & 7;
@@ -273,6 +291,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         if (ok) sT[rb * LDM + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
       }
       __syncthreads();
+      PH(5)
       // BD tile = W tile * Minv : warp owns 8 columns, 4 row tiles
       double bd[4][2];
 #pragma unroll
@@ -287,6 +306,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<double2 *>(sT + (8 * i + g) * LDM + 8 * warp + 2 * t) = make_double2(bd[i][0], bd[i][1]);
       __syncthreads();
+      PH(6)
       // G += BD^T BD on the owned lower-triangle tiles
 #pragma unroll
       for (int jj = 0; jj < kDTB / 4; ++jj) {
@@ -299,6 +319,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           dmma884(gacc[e][0], gacc[e][1], first ? a1 : a2, rowp[8 * J]);
         }
       }
+      PH(7)
     }
     {
       double *Go = G_out + (size_t)w * lay.m_stride;
@@ -314,6 +335,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         }
       }
     }
+    PH(8)
+    PH_PRINT("dense")
   }
 }
 

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "geom.h"
 #include "kernels.h"
@@ -642,7 +643,7 @@ size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw) {
   const int RBMAX = (variant == 0) ? 13 : 4;
   const int NW = (variant == 0) ? 16 : (variant == 1 ? 4 : 8);
   const int R = 8 * RBMAX, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * R * 8 + 64 + 128 +
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + kSolveStages * (R * 8 + 64) +
                            (size_t)nip_max * stw) +
          sizeof(int) * ((size_t)nip_max + 8 * NW + RBMAX * (RBMAX - 1) / 2 + 32 + 8);
 }

@@ -12,6 +12,16 @@
 
 namespace slod {
 
+#ifdef SLOD_PHASE_CLOCKS
+#define PH_DECL long long ph_acc[12] = {0}; long long ph_last = clock64(); const bool ph_on = (blockIdx.x == 0) && ((threadIdx.x & 31) == 0) && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 5);
+#define PH(i) if (ph_on) { const long long c_ = clock64(); ph_acc[i] += c_ - ph_last; ph_last = c_; }
+#define PH_PRINT(tag) if (ph_on) printf(tag " warp %d: %lld %lld %lld %lld %lld %lld | %lld %lld %lld %lld %lld %lld\n", (int)(threadIdx.x >> 5), ph_acc[0], ph_acc[1], ph_acc[2], ph_acc[3], ph_acc[4], ph_acc[5], ph_acc[6], ph_acc[7], ph_acc[8], ph_acc[9], ph_acc[10], ph_acc[11]);
+#else
+#define PH_DECL
+#define PH(i)
+#define PH_PRINT(tag)
+#endif
+
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -26,48 +36,43 @@ __device__ __forceinline__ double c_to_b(double c0, double c1, int lane, int j) 
   return ((lane >> 2) & 1) ? v1 : v0;
 }
 
-// In-register Cholesky of an 8x8 SPD tile held in C layout by one warp; writes L^{-1} (lower, row-major 8x8)
-// to sLinv and uses sLd as scratch.  Returns nonzero if a pivot was not positive.
-__device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double *sLd, double *sLinv) {
+// L^{-1} of the Cholesky factor of an 8x8 SPD tile held in C layout by one warp, all in registers: the row
+// operations of the (LDL^T) elimination are applied to an identity tile M alongside, so that after 8 steps
+// M = Ltilde^{-1} and L^{-1} = D^{-1/2} M.  Only the lower triangle of the tile is read.  Writes L^{-1} (row-major
+// 8x8) to sLinv; returns nonzero if a pivot was not positive.
+__device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double *sLinv) {
   const int g = lane >> 2, t = lane & 3;
+  double m0 = (g == 2 * t) ? 1.0 : 0.0, m1 = (g == 2 * t + 1) ? 1.0 : 0.0;
+  double myinv = 0.0;
   int bad = 0;
-  double rdiag[8];  // 1 / L_kk
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double sel = (k & 1) ? v1 : v0;
+    const double sel = (k & 1) ? v1 : v0;  // column k lives in the lanes with t == k >> 1
     const double dkk = __shfl_sync(0xffffffffu, sel, 4 * k + (k >> 1));
+    const double agk = __shfl_sync(0xffffffffu, sel, 4 * g + (k >> 1));
+    const double ac0 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t) + (k >> 1));
+    const double ac1 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t + 1) + (k >> 1));
+    const double mk0 = __shfl_sync(0xffffffffu, m0, 4 * k + t), mk1 = __shfl_sync(0xffffffffu, m1, 4 * k + t);
     if (!(dkk > 0.0)) bad = 1;
-    const double inv = rsqrt(dkk);
-    rdiag[k] = inv;
-    const double lik = __shfl_sync(0xffffffffu, sel, 4 * g + (k >> 1)) * inv;
-    const double lc0 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t) + (k >> 1)) * inv;
-    const double lc1 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t + 1) + (k >> 1)) * inv;
-    if (2 * t > k) v0 -= lik * lc0;
-    else if (2 * t == k) v0 = lik;
-    if (2 * t + 1 > k) v1 -= lik * lc1;
-    else if (2 * t + 1 == k) v1 = lik;
+    const double rs = rsqrt(dkk);  // off the dependency chain (only the final scaling needs it)
+    myinv = (g == k) ? rs : myinv;
+    // 1 / dkk on the chain: MUFU seed + one cubic Newton step (error ~ e^3, e ~ 2^-20)
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dkk));
+    const double er = fma(-dkk, rc, 1.0);
+    rc = fma(rc, fma(er, er, er), rc);
+    const double mg = (g > k) ? agk * rc : 0.0;
+    v0 -= mg * ac0;
+    v1 -= mg * ac1;
+    m0 -= mg * mk0;
+    m1 -= mg * mk1;
   }
-  sLd[g * 8 + 2 * t] = (2 * t <= g) ? v0 : 0.0;
-  sLd[g * 8 + 2 * t + 1] = (2 * t + 1 <= g) ? v1 : 0.0;
-  sLinv[g * 8 + 2 * t] = 0.0;
-  sLinv[g * 8 + 2 * t + 1] = 0.0;
-  __syncwarp();
-  if (lane < 8) {  // column `lane` of L^{-1} by forward substitution
-    const int j = lane;
-    double x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      double sum = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int tt = 0; tt < 8; ++tt)
-        if (tt < i) sum -= sLd[i * 8 + tt] * ((tt >= j) ? x[tt] : 0.0);
-      x[i] = (i >= j) ? sum * rdiag[i] : 0.0;
-      if (i >= j) sLinv[i * 8 + j] = x[i];
-    }
-  }
+  *reinterpret_cast<double2 *>(sLinv + g * 8 + 2 * t) = make_double2(m0 * myinv, m1 * myinv);
   __syncwarp();
   return bad;
 }
+
+constexpr int kSolveStages = 4;  // backward sweep: L panels staged this many steps ahead (they come back from HBM)
 
 struct SolveMmaLayout {
   int coef_doubles;
@@ -105,10 +110,9 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   double *sCoef = smem;
   double *sWf = sCoef + lay.coef_doubles;   // [R][LDWF] circular dense window of the trailing matrix
   double *sLpT = sWf + R * LDWF;            // [8][LDP]  panel, k-major, slot rows
-  double *sLpR = sLpT + 8 * LDP;            // [2][R*8]  panel rows (row-major by offset) for the backward pass
-  double *sLd = sLpR + 2 * R * 8;           // [64] scratch
-  double *sLinv = sLd + 64;                 // [2][64]
-  double *sSt = sLinv + 128;                // [nip_max][stw] lower stencil values of A_ii, one row per dof
+  double *sLpR = sLpT + 8 * LDP;            // [NSTG][R*8]  panel rows (row-major by offset) for the backward pass
+  double *sLinv = sLpR + kSolveStages * R * 8;  // [NSTG][64]
+  double *sSt = sLinv + kSolveStages * 64;                // [nip_max][stw] lower stencil values of A_ii, one row per dof
   int *sRowPk = (int *)(sSt + (size_t)lay.nip_max * lay.stw);  // [nip_max] packed node coords / comp / mask
   int *sColCell = sRowPk + lay.nip_max;     // [NC] packed cell coords of each coarse column (or -1)
   int *sTileTab = sColCell + NC;            // [NTT] (offI | offJ << 8) of the trailing-update tiles
@@ -175,44 +179,35 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     }
     __syncthreads();
 
-    // write the 8 rows of block `blk` (slot sB) for all live column slots; entries outside the band are zero,
-    // rows >= Ni are identity rows.  One (row, column-slot-block) pair per thread, no divisions.
-    auto assemble_block = [&](int blk, int sB) {
-      for (int pair = tid; pair < 8 * RB; pair += NT) {
-        const int i = pair & 7, sb = pair >> 3;
-        int back = sB - sb;
-        if (back < 0) back += RB;
-        const int cb_abs = blk - back;  // absolute column block living in slot sb
+    // the two coarse columns of this thread's C-fragment entries (constant per patch)
+    const int mycc0 = sColCell[8 * warp + 2 * t], mycc1 = sColCell[8 * warp + 2 * t + 1];
+
+    // Block row `sB` of the window is rebuilt in two phases that an existing barrier separates: all threads zero
+    // it, then the last warps scatter the (at most 14 * spacedim) lower-stencil entries of each of its 8 rows;
+    // rows >= Ni are identity rows.
+    auto zero_block_row = [&](int sB) {
+      for (int item = tid; item < 32 * RB; item += NT) {
+        const int i = item & 7, q = item >> 3;  // row, column pair
+        *reinterpret_cast<double2 *>(sWf + (8 * sB + i) * LDWF + 2 * q) = make_double2(0.0, 0.0);
+      }
+    };
+    auto scatter_block_row = [&](int blk, int sB) {
+      const int per_row = (nlow + 1) * sdim;
+      for (int item = NT - 1 - tid; item < 8 * per_row; item += NT) {
+        const int i = item & 7, ee = item >> 3;
+        const int e = ee / sdim, cb = ee - e * sdim;
         const int r = 8 * blk + i;
-        double out[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = 0.0;
         const int pk = sRowPk[r];
         if (pk < 0) {  // bit 31: a real dof row
-          const int ca = (pk >> 15) & 1, mask = (pk >> 16) & 0x7fff;
-          for (int e = 0; e <= nlow; ++e) {
-            if (!((mask >> e) & 1)) continue;
-            for (int cb = 0; cb < sdim; ++cb) {
-              if (e == nlow && cb > ca) continue;
-              const int c = r + sDOff[e] + (cb - ca);
-              if ((c >> 3) == cb_abs) {
-                const double v = sSt[(size_t)r * stw + e * sdim + cb];
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-                  if (cc == (c & 7)) out[cc] = v;
-              }
-            }
-          }
-        } else if (back == 0) {
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc)
-            if (cc == i) out[cc] = 1.0;
+          const int ca = (pk >> 15) & 1;
+          if (!((pk >> (16 + e)) & 1) || (e == nlow && cb > ca)) continue;
+          const int c = r + sDOff[e] + (cb - ca);
+          int sb = sB - (blk - (c >> 3));
+          if (sb < 0) sb += RB;
+          sWf[(8 * sB + i) * LDWF + 8 * sb + (c & 7)] = sSt[(size_t)r * stw + ee];
+        } else if (ee == 0) {
+          sWf[(8 * sB + i) * LDWF + 8 * sB + i] = 1.0;
         }
-        double2 *dst = reinterpret_cast<double2 *>(sWf + (8 * sB + i) * LDWF + 8 * sb);
-        dst[0] = make_double2(out[0], out[1]);
-        dst[1] = make_double2(out[2], out[3]);
-        dst[2] = make_double2(out[4], out[5]);
-        dst[3] = make_double2(out[6], out[7]);
       }
     };
     // right-hand-side tile (C layout) of block blk for this warp's columns: P_i entries from the tables
@@ -224,7 +219,7 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       const int n = cP.n;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int cc = sColCell[8 * warp + 2 * t + h];
+        const int cc = h ? mycc1 : mycc0;
         if (cc < 0 || ((cc >> 15) & 1) != ca) continue;
         double wgt = cP.pw;
         bool in = true;
@@ -237,23 +232,29 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       }
     };
 
-    double creg[RBMAX][2];
+    // cr[off]: right-hand-side tile (C layout) of block k + off; the window rotates by register moves so that every
+    // index below is static
+    double cr[RBMAX][2];
 #pragma unroll
-    for (int sb = 0; sb < RBMAX; ++sb) {
-      creg[sb][0] = creg[sb][1] = 0.0;
-      if (sb < RB && sb < NBLK) rhs_tile(sb, creg[sb][0], creg[sb][1]);
+    for (int off = 0; off < RBMAX; ++off) {
+      cr[off][0] = cr[off][1] = 0.0;
+      if (off < RB && off < NBLK) rhs_tile(off, cr[off][0], cr[off][1]);
     }
-    for (int b = 0; b < RB && b < NBLK; ++b) assemble_block(b, b);
+    for (int b = 0; b < RB && b < NBLK; ++b) zero_block_row(b);
+    __syncthreads();
+    for (int b = 0; b < RB && b < NBLK; ++b) scatter_block_row(b, b);
     __syncthreads();
     int bad = 0;
     if (warp == 0) {
       const double v0 = sWf[g * LDWF + 2 * t], v1 = sWf[g * LDWF + 2 * t + 1];
-      bad |= chol8_inv(v0, v1, lane, sLd, sLinv);
+      bad |= chol8_inv(v0, v1, lane, sLinv);
     }
     __syncthreads();
 
     // ============================ factorisation + forward substitution ============================
+    PH_DECL
     for (int k = 0, kslot = 0; k < NBLK; ++k, kslot = (kslot + 1 == RB) ? 0 : kslot + 1) {
+      PH(0)
       const int cur = k & 1;
       const double *Linv = sLinv + cur * 64;
       int nl = NBLK - 1 - k;  // live panel blocks below the diagonal block
@@ -277,69 +278,107 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         Ls[32 + lane] = Linv[32 + lane];
       }
       // ---- S2b: Y_D = Linv * R_D for this warp's columns ----
-      double rd0 = 0.0, rd1 = 0.0;
-#pragma unroll
-      for (int sb = 0; sb < RBMAX; ++sb)
-        if (sb == kslot) { rd0 = creg[sb][0]; rd1 = creg[sb][1]; }
       double y0 = 0.0, y1 = 0.0;
       {
-        const double b0 = c_to_b(rd0, rd1, lane, 0), b1 = c_to_b(rd0, rd1, lane, 1);
+        const double b0 = c_to_b(cr[0][0], cr[0][1], lane, 0), b1 = c_to_b(cr[0][0], cr[0][1], lane, 1);
         dmma884(y0, y1, Linv[g * 8 + t], b0);
         dmma884(y0, y1, Linv[g * 8 + 4 + t], b1);
       }
       *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(y0, y1);
       const double yb0 = -c_to_b(y0, y1, lane, 0), yb1 = -c_to_b(y0, y1, lane, 1);
+      // block row kslot (block k) is dead: only its diagonal tile was still needed, by the factorisation of the
+      // previous step.  Clear it for block k + RB; the scatter follows after the barrier.
+      if (k + RB < NBLK) zero_block_row(kslot);
+      PH(1)
       __syncthreads();
+      PH(2)
       // ---- S3: trailing update of the window (shared C), look-ahead factorisation, RHS tiles (register C) ----
       const int ntile = nl * (nl + 1) / 2;
-      // warp 0 owns the look-ahead chain (next diagonal tile + its factorisation); the other tiles go round
-      // robin over warps 1..NW-1
-      for (int tt = (warp == 0) ? 0 : warp; tt < ntile; tt += (warp == 0) ? ntile : NW - 1) {
-        const int tab = sTileTab[tt];
-        const int offI = tab & 0xff, offJ = tab >> 8;
-        int sI = kslot + offI, sJ = kslot + offJ;
-        if (sI >= RB) sI -= RB;
-        if (sJ >= RB) sJ -= RB;
-        double *ct = sWf + (8 * sI + g) * LDWF + 8 * sJ + 2 * t;
-        double2 c = *reinterpret_cast<double2 *>(ct);
-        const double a0 = -sLpT[t * LDP + 8 * sI + g], a1 = -sLpT[(4 + t) * LDP + 8 * sI + g];
-        const double b0 = sLpT[t * LDP + 8 * sJ + g], b1 = sLpT[(4 + t) * LDP + 8 * sJ + g];
-        dmma884(c.x, c.y, a0, b0);
-        dmma884(c.x, c.y, a1, b1);
-        *reinterpret_cast<double2 *>(ct) = c;
-        if (tt == 0) {  // next diagonal block: factor it now (look-ahead), warp 0 only
-          bad |= chol8_inv(c.x, c.y, lane, sLd, sLinv + (cur ^ 1) * 64);
+      if (warp == 0) {
+        // warp 0 owns the look-ahead chain: next diagonal tile, then its factorisation
+        if (ntile > 0) {
+          int sI = kslot + 1;
+          if (sI >= RB) sI -= RB;
+          double *ct = sWf + (8 * sI + g) * LDWF + 8 * sI + 2 * t;
+          double2 c = *reinterpret_cast<double2 *>(ct);
+          const double a0 = -sLpT[t * LDP + 8 * sI + g], a1 = -sLpT[(4 + t) * LDP + 8 * sI + g];
+          dmma884(c.x, c.y, a0, -a0);
+          dmma884(c.x, c.y, a1, -a1);
+          *reinterpret_cast<double2 *>(ct) = c;
+          bad |= chol8_inv(c.x, c.y, lane, sLinv + (cur ^ 1) * 64);
         }
       }
+      // The warps that share warp 0's scheduler hold their DMMAs back until the factorisation chain is through:
+      // its dependent fp64 operations would otherwise queue behind them on the shared fp64 pipe.
+      if ((warp & 3) == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * (NW / 4)) : "memory");
+      if (warp & 3) {
+        // the other tiles go round robin over the warps of the three schedulers warp 0 does not sit on (its
+        // fp64 dependency chain shares the pipe with their DMMAs), three at a time for instruction-level parallelism
+        constexpr int NTW = NW - NW / 4;
+        const int wrank = warp - 1 - (warp >> 2);  // 0 .. NTW-1
+        for (int tt = 1 + wrank; tt < ntile; tt += 3 * NTW) {
+          double *ct[3];
+          double2 c[3];
+          double a0[3], a1[3], b0[3], b1[3];
 #pragma unroll
-      for (int sb = 0; sb < RBMAX; ++sb) {
-        if (sb < RB) {
-          int off = sb - kslot;
-          if (off < 0) off += RB;
-          if (off >= 1 && off <= nl) {
-            const double a0 = sLpT[t * LDP + 8 * sb + g], a1 = sLpT[(4 + t) * LDP + 8 * sb + g];
-            dmma884(creg[sb][0], creg[sb][1], a0, yb0);
-            dmma884(creg[sb][0], creg[sb][1], a1, yb1);
+          for (int u = 0; u < 3; ++u) {
+            const int tu = tt + u * NTW;
+            const int tab = sTileTab[tu < ntile ? tu : tt];
+            const int offI = tab & 0xff, offJ = tab >> 8;
+            int sI = kslot + offI, sJ = kslot + offJ;
+            if (sI >= RB) sI -= RB;
+            if (sJ >= RB) sJ -= RB;
+            ct[u] = sWf + (8 * sI + g) * LDWF + 8 * sJ + 2 * t;
+            c[u] = *reinterpret_cast<double2 *>(ct[u]);
+            a0[u] = -sLpT[t * LDP + 8 * sI + g];
+            a1[u] = -sLpT[(4 + t) * LDP + 8 * sI + g];
+            b0[u] = sLpT[t * LDP + 8 * sJ + g];
+            b1[u] = sLpT[(4 + t) * LDP + 8 * sJ + g];
           }
+#pragma unroll
+          for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a0[u], b0[u]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a1[u], b1[u]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            if (tt + u * NTW < ntile) *reinterpret_cast<double2 *>(ct[u]) = c[u];
         }
       }
-      // ---- slide: block k + RB takes the slot of block k ----
-      if (k + RB < NBLK) {
-        assemble_block(k + RB, kslot);
-        double n0, n1;
-        rhs_tile(k + RB, n0, n1);
+      PH(3)
 #pragma unroll
-        for (int sb = 0; sb < RBMAX; ++sb)
-          if (sb == kslot) { creg[sb][0] = n0; creg[sb][1] = n1; }
+      for (int off = 1; off < RBMAX; ++off) {
+        if (off <= nl) {
+          int sI = kslot + off;
+          if (sI >= RB) sI -= RB;
+          const double a0 = sLpT[t * LDP + 8 * sI + g], a1 = sLpT[(4 + t) * LDP + 8 * sI + g];
+          dmma884(cr[off][0], cr[off][1], a0, yb0);
+          dmma884(cr[off][0], cr[off][1], a1, yb1);
+        }
       }
+      PH(4)
+      // ---- slide: block k + RB takes the slot of block k; the register window moves up by one ----
+      double n0 = 0.0, n1 = 0.0;
+      if (k + RB < NBLK) {
+        scatter_block_row(k + RB, kslot);
+        rhs_tile(k + RB, n0, n1);
+      }
+#pragma unroll
+      for (int off = 0; off < RBMAX - 1; ++off) {
+        cr[off][0] = (off == RB - 1) ? n0 : cr[off + 1][0];
+        cr[off][1] = (off == RB - 1) ? n1 : cr[off + 1][1];
+      }
+      if (RB == RBMAX) { cr[RBMAX - 1][0] = n0; cr[RBMAX - 1][1] = n1; }
+      PH(5)
       __syncthreads();
     }
+    PH(0)
     if (bad && lane == 0) atomicOr(&status[pid], 1);
 
     // ====================================== backward substitution ======================================
-    double xb[RBMAX][2];
+    // xr[off]: B-fragments of the solved block k + off
+    double xr[RBMAX][2];
 #pragma unroll
-    for (int sb = 0; sb < RBMAX; ++sb) xb[sb][0] = xb[sb][1] = 0.0;
+    for (int off = 0; off < RBMAX; ++off) xr[off][0] = xr[off][1] = 0.0;
     auto stage_step = [&](int k, int buf) {  // L workspace of step k -> shared (Linv + panel rows)
       const double *Ls = myL + (size_t)k * LSTEP;
       int nl = NBLK - 1 - k;
@@ -351,31 +390,60 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       }
       __pipeline_commit();
     };
-    stage_step(NBLK - 1, (NBLK - 1) & 1);
-    __pipeline_wait_prior(0);
+    // prologue: stages and Y tiles of the first kSolveStages - 1 steps
+#pragma unroll
+    for (int j = 0; j < kSolveStages - 1; ++j) {
+      if (NBLK - 1 - j >= 0) stage_step(NBLK - 1 - j, (NBLK - 1 - j) & (kSolveStages - 1));
+      else __pipeline_commit();
+    }
+    double2 yq[kSolveStages - 1];
+#pragma unroll
+    for (int j = 0; j < kSolveStages - 1; ++j) {
+      yq[j] = make_double2(0.0, 0.0);
+      if (NBLK - 1 - j >= 0)
+        yq[j] = *reinterpret_cast<const double2 *>(X + (size_t)(8 * (NBLK - 1 - j) + g) * lay.ldx + 8 * warp + 2 * t);
+    }
+    __pipeline_wait_prior(kSolveStages - 2);
     __syncthreads();
-    for (int k = NBLK - 1, kslot = (NBLK - 1) % RB; k >= 0; --k, kslot = (kslot == 0) ? RB - 1 : kslot - 1) {
-      const int buf = k & 1;
+    for (int k = NBLK - 1; k >= 0; --k) {
+      PH(6)
+      const int buf = k & (kSolveStages - 1);
       int nl = NBLK - 1 - k;
       if (nl > RB - 1) nl = RB - 1;
-      if (k > 0) stage_step(k - 1, buf ^ 1);
+      const double2 yv = yq[0];
+#pragma unroll
+      for (int j = 0; j < kSolveStages - 2; ++j) yq[j] = yq[j + 1];
+      yq[kSolveStages - 2] = make_double2(0.0, 0.0);
+      if (k - (kSolveStages - 1) >= 0) {
+        const int kn = k - (kSolveStages - 1);
+        stage_step(kn, kn & (kSolveStages - 1));
+        yq[kSolveStages - 2] =
+            *reinterpret_cast<const double2 *>(X + (size_t)(8 * kn + g) * lay.ldx + 8 * warp + 2 * t);
+      } else {
+        __pipeline_commit();
+      }
       const double *Lp = sLpR + buf * R * 8;
       const double *Linv = sLinv + buf * 64;
-      double2 yv = *reinterpret_cast<const double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t);
-      double c0 = yv.x, c1 = yv.y;
+      // two accumulator chains (odd / even offsets)
+      double c0 = yv.x, c1 = yv.y, e0 = 0.0, e1 = 0.0;
+      PH(7)
 #pragma unroll
-      for (int sb = 0; sb < RBMAX; ++sb) {
-        if (sb < RB) {
-          int off = sb - kslot;
-          if (off < 0) off += RB;
-          if (off >= 1 && off <= nl) {
-            // A = Lp^T : A[m = g][kk = 4j + t] = Lp[8 (off-1) + 4j + t][g]
-            const double a0 = -Lp[(8 * (off - 1) + t) * 8 + g], a1 = -Lp[(8 * (off - 1) + 4 + t) * 8 + g];
-            dmma884(c0, c1, a0, xb[sb][0]);
-            dmma884(c0, c1, a1, xb[sb][1]);
+      for (int off = 1; off < RBMAX; ++off) {
+        if (off <= nl) {
+          // A = Lp^T : A[m = g][kk = 4j + t] = Lp[8 (off-1) + 4j + t][g]
+          const double a0 = -Lp[(8 * (off - 1) + t) * 8 + g], a1 = -Lp[(8 * (off - 1) + 4 + t) * 8 + g];
+          if (off & 1) {
+            dmma884(c0, c1, a0, xr[off][0]);
+            dmma884(c0, c1, a1, xr[off][1]);
+          } else {
+            dmma884(e0, e1, a0, xr[off][0]);
+            dmma884(e0, e1, a1, xr[off][1]);
           }
         }
       }
+      c0 += e0;
+      c1 += e1;
+      PH(8)
       // X_D = Linv^T T
       const double tb0 = c_to_b(c0, c1, lane, 0), tb1 = c_to_b(c0, c1, lane, 1);
       double x0 = 0.0, x1 = 0.0;
@@ -384,11 +452,15 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(x0, x1);
       const double nb0 = c_to_b(x0, x1, lane, 0), nb1 = c_to_b(x0, x1, lane, 1);
 #pragma unroll
-      for (int sb = 0; sb < RBMAX; ++sb)
-        if (sb == kslot) { xb[sb][0] = nb0; xb[sb][1] = nb1; }
-      __pipeline_wait_prior(0);
+      for (int off = RBMAX - 1; off >= 2; --off) { xr[off][0] = xr[off - 1][0]; xr[off][1] = xr[off - 1][1]; }
+      xr[1][0] = nb0;
+      xr[1][1] = nb1;
+      PH(9)
+      __pipeline_wait_prior(kSolveStages - 2);
       __syncthreads();
+      PH(10)
     }
+    PH_PRINT("solve")
   }
 }
 
