@@ -242,23 +242,27 @@ def main():
     for f, t in enumerate(tables):
         ctx.set_coefficient(f, w["r"], t)
     n, s, stride, ellw = ctx.n_patches, w["s"], ctx.basis_stride, ctx.ell_width
-    assert n % world == 0, "patch count must divide over the ranks"
-    p0, p1 = rank * (n // world), (rank + 1) * (n // world)
+    part = importlib.import_module("dealii-slod_b200.partition")
     phi = torch.zeros((n, s, stride), dtype=torch.float64, device=dev)
     aphi = torch.zeros_like(phi)
     K = torch.zeros((n * s, ellw), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    tk = np.zeros(8)
 
-    def step():
+    def run_basis(p0, p1):
         ctx.compute_basis_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), stream)
-        tk = ctx.timings().copy()
-        if world > 1:
-            dist.all_gather_into_tensor(aphi.view(-1), aphi[p0:p1].reshape(-1))
+        tk[:4] = ctx.timings()[:4]
+
+    def run_coarse(p0, p1):
         ctx.assemble_coarse_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), stream)
         tk[4] = ctx.timings()[4]
-        if world > 1:
-            dist.all_gather_into_tensor(K.view(-1), K[p0 * s:p1 * s].reshape(-1))
-        return tk
+
+    job = part.DistributedOffline(dist, rank, world, n, s, phi, aphi, K, run_basis, run_coarse)
+    p0, p1 = job.p0, job.p1
+
+    def step():
+        job.step()
+        return tk.copy()
 
     def barrier():
         torch.cuda.synchronize()
@@ -287,37 +291,59 @@ def main():
     value = n / (ms_step * 1e-3)
     kms = ksum / args.steps          # per-step kernel times of this rank (ms)
 
-    # ---- end to end through the host-buffer C ABI (rank-local share when N > 1) ----
+    # ---- end to end: host buffers in, host buffers out, every copy inside the timed region ----
+    # N = 1: the host-buffer C ABI (what the reference's LOD::run would call).  N > 1: every rank uploads the
+    # coefficient through the C ABI, computes its patch range, takes part in the A*phi all-gather, and brings its own
+    # rows of phi, A*phi and K back into pinned host memory; time = max over ranks.
     e2e = None
     if not args.no_e2e:
-        ctx2 = ctx if world == 1 else None
-        if ctx2 is not None:
+        h2d = sum(t_.size * 8 for t_ in tables) * (2 ** (w["dim"] * max(0, w["ref"] + int(np.log2(w["n"])) - w["r"])))
+        if world == 1:
             def e2e_step():
                 for f, tb in enumerate(tables):
-                    ctx2.set_coefficient(f, w["r"], tb)
-                ctx2.compute_basis()
-                ctx2.assemble_coarse()
-                rowptr, col, val = ctx2.coarse_csr()
-                ph, _ = ctx2.all_basis()
+                    ctx.set_coefficient(f, w["r"], tb)
+                ctx.compute_basis()
+                ctx.assemble_coarse()
+                rowptr, col, val = ctx.coarse_csr()
+                ph, _ = ctx.all_basis()
                 return float(val[0] + ph[0, 0, 0])
-            e2e_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            reps = max(1, min(args.steps, 3))
-            for _ in range(reps):
-                e2e_step()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / reps
-            h2d = sum(t_.size * 8 for t_ in tables) * (2 ** (w["dim"] * max(0, w["ref"] + int(np.log2(w["n"])) - w["r"])))
             d2h = n * s * ellw * 8 + 2 * n * s * stride * 8
-            e2e = {"value": n / dt, "unit": "patches/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": dt * 1e3,
-                   "path": "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_coarse_csr+slod_get_all_basis"}
+            path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_coarse_csr+slod_get_all_basis"
+        else:
+            h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
+            h_aphi = torch.empty_like(h_phi, pin_memory=True)
+            h_K = torch.empty(((p1 - p0) * s, ellw), dtype=torch.float64, pin_memory=True)
+
+            def e2e_step():
+                for f, tb in enumerate(tables):
+                    ctx.set_coefficient(f, w["r"], tb)
+                job.step(gather_K=False)
+                h_phi.copy_(phi[p0:p1], non_blocking=True)
+                h_aphi.copy_(aphi[p0:p1], non_blocking=True)
+                h_K.copy_(K[p0 * s:p1 * s], non_blocking=True)
+                torch.cuda.synchronize()
+                return float(h_K[0, 0] + h_phi[0, 0, 0])
+            d2h = (p1 - p0) * s * (ellw + 2 * stride) * 8 * world
+            path = ("per rank: slod_set_coefficient+slod_compute_basis_device+all_gather(A phi)+"
+                    "slod_assemble_coarse_device+D2H of the rank's rows into pinned memory")
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": n / dt, "unit": "patches/s", "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "path": path}
 
     if rank == 0:
         fm = flop_model(w)
         names = ["patch_solve", "patch_dense", "patch_select", "patch_finish"]
-        share = (n // world) / n
+        share = (p1 - p0) / n
         kern = {}
         for i, nm in enumerate(names):
             if kms[i] > 0:

@@ -506,15 +506,27 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
       for (int i = tid; i < g.Nf; i += NT) sPhi[i] = 0.0;
       __syncthreads();
       double nrm = 0.0;
-      for (int r = warp; r < g.Ni; r += nwarp) {
-        double acc = 0.0;
-        for (int col = lane; col < ncd; col += 32) acc += X[(size_t)r * lay.ldx + col] * sC[col];
-        acc = warp_sum(acc);
+      // four rows of X per warp iteration: 16 independent 256-byte loads in flight per warp
+      for (int r0 = 4 * warp; r0 < g.Ni; r0 += 4 * nwarp) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = min(r0 + u, g.Ni - 1);
+#pragma unroll 4
+          for (int col = lane; col < ncd; col += 32) acc[u] += X[(size_t)r * lay.ldx + col] * sC[col];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
         if (lane == 0) {
-          int a[3], ca;
-          idof_to_node(g, r, a, ca);
-          sPhi[node_index(g, a) * s + ca] = acc;
-          nrm += acc * acc;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (r0 + u < g.Ni) {
+              int a[3], ca;
+              idof_to_node(g, r0 + u, a, ca);
+              sPhi[node_index(g, a) * s + ca] = acc[u];
+              nrm += acc[u] * acc[u];
+            }
+          }
         }
       }
       if (lane == 0) sRed[warp] = nrm;
@@ -540,18 +552,45 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
           if (node_class(cP, g, a) & 2) {
             av = v;  // domain-boundary rows of semi_constrained are identity rows (source/LOD.cc:537-541)
           } else {
-            const int nst = (cP.dim == 3) ? 27 : 9;
-            for (int e = 0; e < nst; ++e) {
-              int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
-              int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
-              bool ok = true;
-              _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) ok = ok && (b[x] >= 0 && b[x] <= g.p[x] - 1);
-              if (!ok) continue;
-              const int nb_ = node_index(g, b);
-              for (int cb = 0; cb < s; ++cb) {
-                const double pv = sPhi[nb_ * s + cb];
-                if (pv != 0.0) av += stiff_entry(cP, g, sCoef, a, dl, ca, cb) * pv;
+            // sub-cell-wise application of the patch operator: for every sub-cell that contains the node, its local
+            // matrix row times the local phi values (include/Diffusion.h:143-193 / include/Elasticity.h:211-284)
+            const int dimv = cP.dim, nn = 1 << dimv, nl = nn * s;
+            const int msx = g.m[0] * cP.n, msy = g.m[1] * cP.n, msz = (dimv == 3) ? g.m[2] * cP.n : 1;
+            const int nsubp = msx * msy * msz;
+            for (int oc = 0; oc < nn; ++oc) {
+              // sub-cell origin = node - (oc bits); the node is local vertex la = oc of that sub-cell
+              const int ox = a[0] - (oc & 1), oy = a[1] - ((oc >> 1) & 1), oz = (dimv == 3) ? a[2] - ((oc >> 2) & 1) : 0;
+              if (ox < 0 || ox >= msx || oy < 0 || oy >= msy || oz < 0 || oz >= msz) continue;
+              const int sc = (oz * msy + oy) * msx + ox;
+              const int rowi = (oc * s + ca) * nl;
+              double cacc = 0.0;
+              if (!cP.gauss_coef) {
+                double racc = 0.0, lacc = 0.0;
+                for (int lb = 0; lb < nn; ++lb) {
+                  const int nb_ = ((oz + ((lb >> 2) & 1)) * g.p[1] + (oy + ((lb >> 1) & 1))) * g.p[0] + ox + (lb & 1);
+                  for (int cb = 0; cb < s; ++cb) {
+                    const double pv = sPhi[nb_ * s + cb];
+                    racc += cP.Kref[rowi + lb * s + cb] * pv;
+                    if (cP.problem != 0) lacc += cP.Klam[rowi + lb * s + cb] * pv;
+                  }
+                }
+                cacc = (cP.problem == 0) ? sCoef[sc] * racc : sCoef[nsubp + sc] * racc + sCoef[sc] * lacc;
+              } else {
+                for (int q = 0; q < nn; ++q) {
+                  double racc = 0.0, lacc = 0.0;
+                  for (int lb = 0; lb < nn; ++lb) {
+                    const int nb_ = ((oz + ((lb >> 2) & 1)) * g.p[1] + (oy + ((lb >> 1) & 1))) * g.p[0] + ox + (lb & 1);
+                    for (int cb = 0; cb < s; ++cb) {
+                      const double pv = sPhi[nb_ * s + cb];
+                      racc += cP.Kq[q][rowi + lb * s + cb] * pv;
+                      if (cP.problem != 0) lacc += cP.Klamq[q][rowi + lb * s + cb] * pv;
+                    }
+                  }
+                  cacc += (cP.problem == 0) ? sCoef[sc * nn + q] * racc
+                                            : sCoef[(nsubp + sc) * nn + q] * racc + sCoef[sc * nn + q] * lacc;
+                }
               }
+              av += cacc;
             }
           }
         }
@@ -604,14 +643,19 @@ k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const d
         if (valid) {
           const double *aq = aphi + ((size_t)qid * s + e) * lay.nf_max;
           const double *pp = sPhi + d * lay.nf_max;
-          const int ex = b1[0] - b0[0] + 1, ey = b1[1] - b0[1] + 1;
+          const int ex = b1[0] - b0[0] + 1, ey = b1[1] - b0[1] + 1, ez = b1[2] - b0[2] + 1;
+          // lanes sweep the (x, y) plane of the overlap box; the z loop only adds plane strides
+          const int sp_ = g.p[0] * g.p[1] * s, sq_ = gq.p[0] * gq.p[1] * s;
+          const int op = (((b0[2] - g.lo[2] * n) * g.p[1] + (b0[1] - g.lo[1] * n)) * g.p[0] + (b0[0] - g.lo[0] * n)) * s;
+          const int oq = (((b0[2] - gq.lo[2] * n) * gq.p[1] + (b0[1] - gq.lo[1] * n)) * gq.p[0] + (b0[0] - gq.lo[0] * n)) * s;
+          const int exs = ex * s;
           double acc = 0.0;
-          for (int t = lane; t < cnt; t += 32) {
-            const int ix = t % ex, iy = (t / ex) % ey, iz = t / (ex * ey);
-            const int gx = b0[0] + ix, gy = b0[1] + iy, gz = b0[2] + iz;
-            const int np_ = ((gz - g.lo[2] * n) * g.p[1] + (gy - g.lo[1] * n)) * g.p[0] + (gx - g.lo[0] * n);
-            const int nq_ = ((gz - gq.lo[2] * n) * gq.p[1] + (gy - gq.lo[1] * n)) * gq.p[0] + (gx - gq.lo[0] * n);
-            for (int c = 0; c < s; ++c) acc += pp[np_ * s + c] * aq[nq_ * s + c];
+          for (int t = lane; t < exs * ey; t += 32) {
+            const int iy = t / exs, ix = t - iy * exs;   // ix runs over (node, component)
+            const double *p1 = pp + op + iy * g.p[0] * s + ix;
+            const double *q1 = aq + oq + iy * gq.p[0] * s + ix;
+#pragma unroll 4
+            for (int iz = 0; iz < ez; ++iz) acc += p1[iz * sp_] * q1[iz * sq_];
           }
           val = warp_sum(acc);
         }
