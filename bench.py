@@ -305,9 +305,11 @@ def main():
                 ctx.compute_basis()
                 ctx.assemble_coarse()
                 rowptr, col, val = ctx.coarse_csr()
-                ph, _ = ctx.all_basis()
+                ph, aph = ctx.all_basis()
+                e2e_bytes[0] = val.nbytes + ph.nbytes + aph.nbytes
                 return float(val[0] + ph[0, 0, 0])
-            d2h = n * s * ellw * 8 + 2 * n * s * stride * 8
+            e2e_bytes = [0]
+            d2h = None
             path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_coarse_csr+slod_get_all_basis"
         else:
             h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
@@ -337,6 +339,8 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
+        if d2h is None:
+            d2h = e2e_bytes[0]   # CSR values + phi + A*phi (rowptr / col are integer geometry cached on the host)
         e2e = {"value": n / dt, "unit": "patches/s", "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "path": path}
 

@@ -25,7 +25,8 @@ EXPORTS = [
     "slod_get_patch_local_dofs", "slod_get_patch_dof_class", "slod_compute_basis", "slod_get_basis",
     "slod_basis_stride", "slod_get_all_basis", "slod_assemble_coarse", "slod_get_coarse_csr",
     "slod_get_patch_diagnostics", "slod_debug_patch_stages", "slod_get_timings", "slod_compute_basis_device",
-    "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count",
+    "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
+    "slod_free_host",
 ]
 
 
@@ -82,6 +83,8 @@ def load_library():
     lib.slod_ell_width.argtypes = [vp, P(i64)]
     lib.slod_ell_to_csr.argtypes = [vp, P(dbl), P(i64), P(i64), P(dbl), P(i64), P(i64)]
     lib.slod_launch_count.argtypes = [vp, P(i64)]
+    lib.slod_alloc_host.argtypes = [C.c_size_t, P(vp)]
+    lib.slod_free_host.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -105,9 +108,31 @@ class SlodContext:
         self.dim, self.s = dim, spacedim
 
     def close(self):
+        for ptr in getattr(self, "_pinned_ptrs", []):
+            self.lib.slod_free_host(ptr)
+        self._pinned_ptrs, self._pinned = [], {}
         if getattr(self, "h", None) and self.h.value:
             self.lib.slod_destroy(self.h)
             self.h = C.c_void_p()
+
+    def _out(self, key, shape, dtype=np.float64):
+        """Output array in page-locked memory (slod_alloc_host), allocated once per key and reused by later calls."""
+        if not hasattr(self, "_pinned"):
+            self._pinned, self._pinned_ptrs = {}, []
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        arr = self._pinned.get(key)
+        if arr is not None and arr.shape == shape and arr.dtype == dtype:
+            return arr
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        if self.par.device == -2 or self.lib.slod_alloc_host(nbytes, C.byref(ptr)) != SLOD_OK:
+            arr = np.empty(shape, dtype=dtype)                       # maps-only handle / allocation refused
+        else:
+            self._pinned_ptrs.append(ptr)
+            buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+            arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned[key] = arr
+        return arr
 
     def __del__(self):
         try:
@@ -190,8 +215,8 @@ class SlodContext:
 
     def all_basis(self):
         shape = (self.n_patches, self.s, self.basis_stride)
-        phi = np.empty(shape)
-        aphi = np.empty(shape)
+        phi = self._out("phi", shape)
+        aphi = self._out("aphi", shape)
         self._ck(self.lib.slod_get_all_basis(self.h, _dp(phi), _dp(aphi)))
         return phi, aphi
 
@@ -201,9 +226,9 @@ class SlodContext:
     def coarse_csr(self):
         nr, nnz = C.c_int64(), C.c_int64()
         self._ck(self.lib.slod_get_coarse_csr(self.h, None, None, None, C.byref(nr), C.byref(nnz)))
-        rowptr = np.empty(nr.value + 1, dtype=np.int64)
-        col = np.empty(nnz.value, dtype=np.int64)
-        val = np.empty(nnz.value)
+        rowptr = self._out("rowptr", nr.value + 1, np.int64)
+        col = self._out("col", nnz.value, np.int64)
+        val = self._out("val", nnz.value)
         i64p = C.POINTER(C.c_int64)
         self._ck(self.lib.slod_get_coarse_csr(self.h, rowptr.ctypes.data_as(i64p), col.ctypes.data_as(i64p),
                                               _dp(val), C.byref(nr), C.byref(nnz)))

@@ -41,6 +41,7 @@ struct slod_ctx {
   int coef_r[2] = {0, 0};
   bool coef_dirty = true;
   double *d_coef = nullptr;  // [n_fields][nsub^dim]
+  size_t d_coef_elems = 0;
   size_t coef_field_elems = 0;
   // results owned by the handle (host-buffer API)
   double *d_phi = nullptr, *d_aphi = nullptr, *d_Kell = nullptr, *d_diag = nullptr;
@@ -68,10 +69,17 @@ struct slod_ctx {
   cudaEvent_t ev[10]{};
   Timings tm;
   int64_t launches = 0;
+  std::vector<int> ids;   // cost-sorted work list of the last patch range
+  int64_t ids_p0 = -1, ids_p1 = -1;
   mutable std::string err;
   // host caches
   mutable std::vector<int64_t> fine_numbering;  // global node -> deal.II dof of comp 0
-  std::vector<double> h_Kell;
+  // CSR pattern of the coarse matrix (integer geometry: built once per handle) and the compacted values
+  bool csr_ready = false;
+  std::vector<int64_t> csr_rowptr, csr_col;
+  long long *d_perm = nullptr;   // CSR entry -> position in the block-ELL array
+  double *d_val = nullptr;
+  int64_t csr_nnz = 0;
 };
 
 namespace {
@@ -235,6 +243,7 @@ void free_dev(slod_ctx *c) {
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
   F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
+  F(c->d_perm); F(c->d_val);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
 }
 
@@ -277,9 +286,12 @@ int prepare_coefficients(slod_ctx *ctx) {
             out[(((size_t)z * ns + y) * ns + x) * nq + q] = tab[((size_t)iz * nl + iy) * nl + ix];
           }
   }
-  if (ctx->d_coef) cudaFree(ctx->d_coef);
-  ctx->d_coef = nullptr;
-  CK(cudaMalloc(&ctx->d_coef, sizeof(double) * fine.size()));
+  if (ctx->d_coef && ctx->d_coef_elems != fine.size()) {
+    cudaFree(ctx->d_coef);
+    ctx->d_coef = nullptr;
+  }
+  if (!ctx->d_coef) CK(cudaMalloc(&ctx->d_coef, sizeof(double) * fine.size()));
+  ctx->d_coef_elems = fine.size();
   CK(cudaMemcpy(ctx->d_coef, fine.data(), sizeof(double) * fine.size(), cudaMemcpyHostToDevice));
   P.gauss_coef = gauss;
   ctx->coef_dirty = false;
@@ -338,19 +350,24 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
   rc = ensure_workspace(ctx, p1 - p0);
   if (rc) return rc;
   CK(upload_params(P));
-  // work order: largest patches first
-  std::vector<int> order((size_t)(p1 - p0));
-  std::iota(order.begin(), order.end(), (int)p0);
-  std::vector<long long> cost(order.size());
-  for (size_t i = 0; i < order.size(); ++i) {
-    const Geom g = make_geom(P, order[i]);
-    cost[i] = (long long)g.Ni * g.bw * (g.bw + 4LL * g.Ncd) + (long long)g.Ncd * g.Ncd * g.Ncd * 8;
+  // work order: largest patches first (integer geometry: cached per range)
+  if (ctx->ids_p0 != p0 || ctx->ids_p1 != p1) {
+    std::vector<int> order((size_t)(p1 - p0));
+    std::iota(order.begin(), order.end(), (int)p0);
+    std::vector<long long> cost(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+      const Geom g = make_geom(P, order[i]);
+      cost[i] = (long long)g.Ni * g.bw * (g.bw + 4LL * g.Ncd) + (long long)g.Ncd * g.Ncd * g.Ncd * 8;
+    }
+    std::vector<int> perm(order.size());
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    ctx->ids.resize(order.size());
+    for (size_t i = 0; i < perm.size(); ++i) ctx->ids[i] = order[perm[i]];
+    ctx->ids_p0 = p0;
+    ctx->ids_p1 = p1;
   }
-  std::vector<int> perm(order.size());
-  std::iota(perm.begin(), perm.end(), 0);
-  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  std::vector<int> ids(order.size());
-  for (size_t i = 0; i < perm.size(); ++i) ids[i] = order[perm[i]];
+  const std::vector<int> &ids = ctx->ids;
 
   float acc[4] = {0, 0, 0, 0};
   for (size_t off = 0; off < ids.size(); off += ctx->chunk) {
@@ -411,7 +428,7 @@ int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const
 
 // block-ELL -> CSR.  The pattern is integer geometry: (p, q) is structural iff the node boxes intersect.
 int ell_to_csr(const slod_ctx *ctx, const double *hK, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
-               int64_t *nnz) {
+               int64_t *nnz, long long *perm = nullptr) {
   const Params &P = ctx->P;
   const int s = P.s, w = P.w, ww = 2 * w + 1;
   const int nslots = (P.dim == 3) ? ww * ww * ww : ww * ww;
@@ -456,7 +473,7 @@ int ell_to_csr(const slod_ctx *ctx, const double *hK, int64_t *rowptr, int64_t *
   for (int64_t p = 0; p < np; ++p) start[p + 1] = start[p] + cnt[p + 1] * s * s;
   if (nnz) *nnz = start[np];
   if (!rowptr) return SLOD_OK;
-  if (!col || !val || !hK) return fail(ctx, SLOD_ERR_INVALID, "null output buffer");
+  if (!col || (!perm && (!val || !hK))) return fail(ctx, SLOD_ERR_INVALID, "null output buffer");
   {
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nthr; ++t)
@@ -469,11 +486,12 @@ int ell_to_csr(const slod_ctx *ctx, const double *hK, int64_t *rowptr, int64_t *
             const int64_t r = pid * s + d;
             int64_t o = start[pid] + d * per_row;
             rowptr[r] = o;
-            const double *krow = hK + (size_t)r * P.ell_width;
+            const double *krow = hK ? hK + (size_t)r * P.ell_width : nullptr;
             for (const auto &q : nb)
               for (int e = 0; e < s; ++e) {
                 col[o] = (int64_t)q.first * s + e;
-                val[o] = krow[q.second * s + e];
+                if (perm) perm[o] = (long long)r * P.ell_width + q.second * s + e;
+                else val[o] = krow[q.second * s + e];
                 ++o;
               }
           }
@@ -693,7 +711,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   };
   ctx->grid_solve = ctx->n_sm * per_sm(ctx->smem_solve, sl.threads);
   ctx->grid_dense = ctx->n_sm * per_sm(ctx->smem_dense, dl.threads);
-  sp.grid_fast = ctx->n_sm * per_sm(sp.smem_fast, sp.lay.threads);
+  sp.grid_fast = ctx->n_sm * std::min(3, per_sm(sp.smem_fast, 256));
   sp.grid_jac = ctx->n_sm * per_sm(sp.smem_jac, sp.lay.threads);
   sp.grid_tri = ctx->n_sm * per_sm(sp.smem_tri, 256);
   sp.grid_fin = ctx->n_sm * per_sm(sp.smem_fin, 128);
@@ -952,6 +970,41 @@ int slod_get_all_basis(const slod_ctx *ctx, double *phi, double *aphi) {
   return SLOD_OK;
 }
 
+// CSR pattern + ELL->CSR permutation: integer geometry, built on the first call and kept for the life of the handle
+static int build_csr_cache(slod_ctx *ctx) {
+  if (ctx->csr_ready) return SLOD_OK;
+  int64_t n_rows = 0, nnz = 0;
+  int rc = ell_to_csr(ctx, nullptr, nullptr, nullptr, nullptr, &n_rows, &nnz);
+  if (rc) return rc;
+  ctx->csr_rowptr.resize((size_t)n_rows + 1);
+  ctx->csr_col.resize((size_t)nnz);
+  std::vector<long long> perm((size_t)nnz);
+  rc = ell_to_csr(ctx, nullptr, ctx->csr_rowptr.data(), ctx->csr_col.data(), nullptr, &n_rows, &nnz, perm.data());
+  if (rc) return rc;
+  CK(cudaMalloc(&ctx->d_perm, sizeof(long long) * std::max<size_t>(1, (size_t)nnz)));
+  CK(cudaMalloc(&ctx->d_val, sizeof(double) * std::max<size_t>(1, (size_t)nnz)));
+  CK(cudaMemcpy(ctx->d_perm, perm.data(), sizeof(long long) * (size_t)nnz, cudaMemcpyHostToDevice));
+  ctx->csr_nnz = nnz;
+  ctx->csr_ready = true;
+  return SLOD_OK;
+}
+
+static void parallel_copy(void *dst, const void *src, size_t bytes) {
+  const unsigned nthr = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  if (bytes < ((size_t)8 << 20) || nthr == 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (bytes + nthr - 1) / nthr;
+  for (unsigned t = 0; t < nthr; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    th.emplace_back([=]() { std::memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off)); });
+  }
+  for (auto &x : th) x.join();
+}
+
 int slod_assemble_coarse(slod_ctx *ctx) {
   if (!ctx) return SLOD_ERR_INVALID;
   NEED_DEVICE();
@@ -961,17 +1014,50 @@ int slod_assemble_coarse(slod_ctx *ctx) {
   if (!ctx->d_Kell) CK(cudaMalloc(&ctx->d_Kell, sizeof(double) * n));
   int rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0);
   if (rc) return rc;
-  ctx->h_Kell.resize(n);
-  CK(cudaMemcpy(ctx->h_Kell.data(), ctx->d_Kell, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  rc = build_csr_cache(ctx);
+  if (rc) return rc;
+  CK(launch_gather(0, ctx->d_Kell, ctx->d_perm, ctx->d_val, ctx->csr_nnz));   // compact block-ELL -> CSR values
+  ctx->launches += 1;
+  CK(cudaDeviceSynchronize());
   ctx->coarse_done = true;
   return SLOD_OK;
 }
 
-int slod_get_coarse_csr(const slod_ctx *ctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
+int slod_get_coarse_csr(const slod_ctx *cctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
                         int64_t *nnz) {
-  if (!ctx) return SLOD_ERR_INVALID;
-  if (rowptr && !ctx->coarse_done) return fail(ctx, SLOD_ERR_STATE, "slod_assemble_coarse has not run");
-  return ell_to_csr(ctx, ctx->h_Kell.data(), rowptr, col, val, n_rows, nnz);
+  if (!cctx) return SLOD_ERR_INVALID;
+  slod_ctx *ctx = const_cast<slod_ctx *>(cctx);   // the pattern cache is filled lazily
+  if (!rowptr) {
+    if (ctx->csr_ready) {
+      if (n_rows) *n_rows = (int64_t)ctx->csr_rowptr.size() - 1;
+      if (nnz) *nnz = ctx->csr_nnz;
+      return SLOD_OK;
+    }
+    return ell_to_csr(ctx, nullptr, nullptr, nullptr, nullptr, n_rows, nnz);
+  }
+  NEED_DEVICE();
+  if (!ctx->coarse_done) return fail(ctx, SLOD_ERR_STATE, "slod_assemble_coarse has not run");
+  if (!col || !val) return fail(ctx, SLOD_ERR_INVALID, "null output buffer");
+  CK(cudaSetDevice(ctx->device));
+  if (n_rows) *n_rows = (int64_t)ctx->csr_rowptr.size() - 1;
+  if (nnz) *nnz = ctx->csr_nnz;
+  CK(cudaMemcpyAsync(val, ctx->d_val, sizeof(double) * (size_t)ctx->csr_nnz, cudaMemcpyDeviceToHost, 0));
+  std::memcpy(rowptr, ctx->csr_rowptr.data(), sizeof(int64_t) * ctx->csr_rowptr.size());
+  parallel_copy(col, ctx->csr_col.data(), sizeof(int64_t) * ctx->csr_col.size());
+  CK(cudaStreamSynchronize(0));
+  return SLOD_OK;
+}
+
+/* pinned host memory for the caller-owned output buffers (device->host copies into pageable memory run at a
+ * fraction of the link speed) */
+int slod_alloc_host(size_t bytes, void **out) {
+  if (!out) return SLOD_ERR_INVALID;
+  *out = nullptr;
+  return cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? SLOD_OK : SLOD_ERR_CUDA;
+}
+int slod_free_host(void *p) {
+  if (!p) return SLOD_OK;
+  return cudaFreeHost(p) == cudaSuccess ? SLOD_OK : SLOD_ERR_CUDA;
 }
 
 int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,

@@ -481,7 +481,7 @@ namespace slod {
 // ------------------------------------------------------------------------------------------------
 // k_patch_finish : phi = X c (zero on every boundary dof), normalise, A phi
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
                const double *__restrict__ Xbuf, const double *__restrict__ cvec, double *__restrict__ phi_out,
                double *__restrict__ aphi_out, FinishLayout lay) {
@@ -736,7 +736,9 @@ cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_
   return cudaErrorInvalidValue;
 }
 
-size_t select_fast_smem(int ncd_max) { return sizeof(double) * ((size_t)ncd_max * ncd_max + 4 * (size_t)ncd_max); }
+size_t select_fast_smem(int ncd_max) {
+  return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + 4 * (size_t)ncd_max);
+}
 size_t select_jacobi_smem(int ncd_max) {
   return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + (size_t)ncd_max * ncd_max + 6 * (size_t)ncd_max) +
          sizeof(int) * (3 * (size_t)ncd_max + 8);
@@ -756,7 +758,7 @@ cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const 
   SLOD_ATTR(k_select_fast, pl.smem_fast);
   SLOD_ATTR(k_select_jacobi, pl.smem_jac);
   if ((e = cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st)) != cudaSuccess) return e;
-  k_select_fast<<<min(n_work, pl.grid_fast), pl.lay.threads, pl.smem_fast, st>>>(
+  k_select_fast<<<min(n_work, pl.grid_fast), 256, pl.smem_fast, st>>>(
       ids, n_work, Minv, G, cvec, diag, b.counters, pl.use_ql ? b.eig_list : b.jac_list, pl.use_ql ? 1 : 2, pl.lay);
   ++*n_launches;
   if (pl.use_ql) {
@@ -785,6 +787,16 @@ cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const in
   cudaError_t e = cudaFuncSetAttribute(k_patch_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_patch_finish<<<grid, 256, smem, st>>>(ids, n_work, coef, X, cvec, phi, aphi, lay);
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256)
+k_gather(const double *__restrict__ src, const long long *__restrict__ perm, double *__restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[perm[i]];
+}
+cudaError_t launch_gather(cudaStream_t st, const double *src, const long long *perm, double *dst, long long n) {
+  if (n <= 0) return cudaSuccess;
+  k_gather<<<148 * 8, 256, 0, st>>>(src, perm, dst, n);
   return cudaGetLastError();
 }
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,

@@ -93,6 +93,7 @@ cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const 
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                 const double *X, const double *cvec, double *phi, double *aphi,
                                 const FinishLayout &lay);
+cudaError_t launch_gather(cudaStream_t st, const double *src, const long long *perm, double *dst, long long n);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);
 

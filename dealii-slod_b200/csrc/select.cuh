@@ -27,20 +27,20 @@ __device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 
 // ------------------------------------------------------------------------------------------------
 // k_select_fast
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256, 3)
 k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ Minv_in,
               const double *__restrict__ G_in, double *__restrict__ cvec, double *__restrict__ diag,
               int *__restrict__ counters, int *__restrict__ work_list, int list_slot, SelectLayout lay) {
   extern __shared__ double smem[];
   const int nmax = lay.ncd_max;
-  double *Lc = smem;                       // [n][n]
-  double *sg = Lc + (size_t)nmax * nmax;   // g
-  double *sd = sg + nmax;                  // d
-  double *slam = sd + nmax;                // sqrt of the pivots
-  double *scol = slam + nmax;              // scaled pivot column
+  double *Lc = smem;                                   // packed lower triangle, row i at i (i + 1) / 2
+  double *sg = Lc + (size_t)nmax * (nmax + 1) / 2;     // g
+  double *sd = sg + nmax;                              // d
+  double *slam = sd + nmax;                            // sqrt of the pivots
+  double *scol = slam + nmax;                          // scaled pivot column
   __shared__ int sFlag;
   __shared__ int sWork;
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NWARP = NT >> 5;
   for (;;) {
     __syncthreads();
     if (tid == 0) sWork = atomicAdd(&counters[0], 1);
@@ -64,33 +64,34 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
       const int n = ncd - 1;  // considered_candidates: all coarse dofs but d (source/LOD.cc:637-640)
       bool done = false;
       if (lay.fast_path) {
-        for (int idx = tid; idx < n * n; idx += NT) {
-          const int i = idx / n, j = idx - i * n;
-          Lc[idx] = (j <= i) ? Gf[(i + (i >= d)) * ncd + (j + (j >= d))] : 0.0;
+        for (int i = warp; i < n; i += NWARP) {
+          const double *grow = Gf + (size_t)(i + (i >= d)) * ncd;
+          for (int j = lane; j <= i; j += 32) Lc[i * (i + 1) / 2 + j] = grow[j + (j >= d)];
         }
         for (int i = tid; i < n; i += NT) { sg[i] = Gf[(i + (i >= d)) * ncd + d]; sd[i] = -sg[i]; }
         if (tid == 0) sFlag = 0;
         __syncthreads();
         double dmax = 0.0, pmin = 1e300;
-        for (int i = 0; i < n; ++i) dmax = fmax(dmax, Lc[i * n + i]);
+        for (int i = 0; i < n; ++i) dmax = fmax(dmax, Lc[i * (i + 1) / 2 + i]);
         for (int k = 0; k < n; ++k) {
           __syncthreads();
-          const double akk = Lc[k * n + k];
+          const double akk = Lc[k * (k + 1) / 2 + k];
           pmin = fmin(pmin, akk);
-          const double inv = 1.0 / sqrt(akk);
+          const double inv = rsqrt(akk);
           for (int i = k + 1 + tid; i < n; i += NT) {
-            const double v = Lc[i * n + k] * inv;
-            Lc[i * n + k] = v;
+            const double v = Lc[i * (i + 1) / 2 + k] * inv;
+            Lc[i * (i + 1) / 2 + k] = v;
             scol[i] = v;
           }
           if (tid == 0) slam[k] = akk * inv;
           __syncthreads();
           const int m = n - k - 1;
-          // row i = k+1+warp.., columns by lane: no integer divisions, conflict-free rows
-          for (int ii = warp; ii < m; ii += (NT >> 5)) {
+          // row i = k+1+warp.., columns by lane: no integer divisions, consecutive addresses
+          for (int ii = warp; ii < m; ii += NWARP) {
             const int i = k + 1 + ii;
             const double lik = scol[i];
-            for (int j = k + 1 + lane; j <= i; j += 32) Lc[i * n + j] -= lik * scol[j];
+            double *row = Lc + i * (i + 1) / 2;
+            for (int j = k + 1 + lane; j <= i; j += 32) row[j] -= lik * scol[j];
           }
         }
         __syncthreads();
@@ -100,14 +101,15 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
             const double zk = sd[k] / slam[k];
             __syncwarp();
             if (lane == 0) sd[k] = zk;
-            for (int i = k + 1 + lane; i < n; i += 32) sd[i] -= Lc[i * n + k] * zk;
+            for (int i = k + 1 + lane; i < n; i += 32) sd[i] -= Lc[i * (i + 1) / 2 + k] * zk;
             __syncwarp();
           }
           for (int k = n - 1; k >= 0; --k) {
             const double xk = sd[k] / slam[k];
             __syncwarp();
             if (lane == 0) sd[k] = xk;
-            for (int j = lane; j < k; j += 32) sd[j] -= Lc[k * n + j] * xk;
+            const double *row = Lc + k * (k + 1) / 2;
+            for (int j = lane; j < k; j += 32) sd[j] -= row[j] * xk;
             __syncwarp();
           }
           double m = 0.0;
@@ -120,7 +122,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
         }
         __syncthreads();
         if (sFlag) {
-          for (int i = warp; i < ncd; i += (NT >> 5)) {
+          for (int i = warp; i < ncd; i += NWARP) {
             double acc = 0.0;
             for (int k = lane; k < n; k += 32) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
             acc = warp_sum(acc);

@@ -110,6 +110,11 @@ int slod_assemble_coarse(slod_ctx *ctx);
 int slod_get_coarse_csr(const slod_ctx *ctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
                         int64_t *nnz);
 
+/* Page-locked host memory for the caller-owned output buffers of slod_get_all_basis / slod_get_coarse_csr: copies
+ * into pageable memory work too but run at a fraction of the link speed.  No reference counterpart. */
+int slod_alloc_host(size_t bytes, void **out);
+int slod_free_host(void *p);
+
 /* diagnostics: per patch and component 8 doubles:
  *   [0] ||d||_inf before truncation  [1] truncation steps  [2] sigma_0  [3] smallest kept sigma
  *   [4] cond(M) estimate (max/min Cholesky pivot squared) [5] selection path (0 LOD, 1 Cholesky, 2 eigen)
