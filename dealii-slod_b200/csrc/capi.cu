@@ -63,7 +63,8 @@ struct slod_ctx {
   SelectPlan sp{};
   SelectBuffers sb{};
   FinishLayout fl{};
-  size_t smem_solve = 0, smem_dense = 0, smem_finish = 0, smem_coarse = 0;
+  size_t smem_solve = 0, smem_dense = 0, smem_finish = 0, smem_coarse = 0, smem_coarse_blk = 0;
+  int coarse_nu = 0;   // > 0: blocked coarse kernel with this common-box width
   int grid_solve = 0, grid_dense = 0, grid_finish = 0, grid_coarse = 0;
   int bw_max = 0, nb_max = 0;
   cudaEvent_t ev[10]{};
@@ -415,8 +416,12 @@ int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const
   if (p0 == p1) return SLOD_OK;
   CK(upload_params(ctx->P));
   CK(cudaEventRecord(ctx->ev[5], st));
-  CK(launch_coarse((int)std::min<int64_t>(p1 - p0, ctx->grid_coarse), ctx->smem_coarse, st, (int)p0, (int)p1, d_phi,
-                   d_aphi, d_K, ctx->fl));
+  if (ctx->coarse_nu > 0)
+    CK(launch_coarse_blocked(ctx->P.dim, ctx->P.s, ctx->n_sm, ctx->smem_coarse_blk, st, (int)p0, (int)p1, d_phi, d_aphi,
+                             d_K, ctx->fl, ctx->coarse_nu));
+  else
+    CK(launch_coarse((int)std::min<int64_t>(p1 - p0, ctx->grid_coarse), ctx->smem_coarse, st, (int)p0, (int)p1, d_phi,
+                     d_aphi, d_K, ctx->fl));
   CK(cudaEventRecord(ctx->ev[6], st));
   ctx->launches += 1;
   CK(cudaEventSynchronize(ctx->ev[6]));
@@ -693,10 +698,20 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   // the tridiagonalisation keeps columns of up to 256 rows in registers and the whole matrix in shared memory
   sp.use_ql = (P.NcdMax - 1 <= 256 && sp.smem_tri <= prop.sharedMemPerBlockOptin && !getenv("SLOD_FORCE_JACOBI")) ? 1 : 0;
   FinishLayout &fl = ctx->fl;
+  fl.ell_width = P.ell_width;
   fl.coef_doubles = coef_doubles; fl.nf_max = P.NfMax; fl.ncd_max = P.NcdMax; fl.ldx = sl.ldx; fl.x_stride = sl.x_stride;
   ctx->smem_finish = sizeof(double) * ((size_t)coef_doubles + P.NfMax + P.NcdMax);
   ctx->smem_coarse = sizeof(double) * ((size_t)P.s * P.NfMax);
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
+  {
+    // blocked coarse kernel: the 2^dim patches of a Morton block share a node box of (2 ell + 2) n + 1 nodes per axis
+    const int nu = std::min((2 * P.ell + 2), P.N) * P.n + 1;
+    const size_t sm = coarse_blocked_smem(P.dim, P.s, nu);
+    if (P.ref >= 1 && sm + 2048 <= smem_cap && !getenv("SLOD_SIMPLE_COARSE")) {
+      ctx->coarse_nu = nu;
+      ctx->smem_coarse_blk = sm;
+    }
+  }
   if ((size_t)P.NcdMax * P.NcdMax > (size_t)32 * dl.threads)
     { delete ctx; return bad(SLOD_ERR_UNSUPPORTED, "patch too large: coarse dofs per patch exceed the Gram register tile"); }
   if (ctx->smem_solve > smem_cap || ctx->smem_dense > smem_cap || sp.smem_fast > smem_cap || sp.smem_jac > smem_cap ||

@@ -666,6 +666,160 @@ k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const d
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_coarse_blocked : the same rows, one CTA per Morton-aligned group of 2^dim patches.
+// The basis functions of the group are staged in shared memory on the group's common node box (zero outside
+// each member's own box), so every A*phi value of a neighbour is loaded once per group and multiplied with all
+// members' phi at the same shared-memory offset: no per-pair index arithmetic, 2^dim times less L2 traffic.
+// ------------------------------------------------------------------------------------------------
+template <int DIM, int S>
+__global__ void __launch_bounds__(512, 1)
+k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi, const double *__restrict__ aphi,
+                 double *__restrict__ Kell, FinishLayout lay, int NU) {
+  constexpr int NG = 1 << DIM;   // patches per group
+  constexpr int NA = NG * S;     // accumulators per lane: (member, component d)
+  extern __shared__ double smem[];
+  const int NUV = (DIM == 3) ? NU * NU * NU : NU * NU;
+  double *sU = smem;  // [NA][NUV][S]
+  __shared__ int sGeo[NG][8];  // per member: lo[3] (coarse), centre[3] (coarse), pid, in-range flag
+  __shared__ int sUlo[3], sUhi[3];
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int n = cP.n, w = cP.w, ww = 2 * w + 1;
+  const int g0 = patch_begin >> DIM, g1 = ((patch_end - 1) >> DIM) + 1;
+  for (int grp = g0 + blockIdx.x; grp < g1; grp += gridDim.x) {
+    __syncthreads();
+    if (tid < NG) {
+      const int pid = grp * NG + tid;
+      const Geom g = make_geom(cP, pid);
+      for (int a = 0; a < 3; ++a) { sGeo[tid][a] = g.lo[a]; sGeo[tid][3 + a] = g.lo[a] + g.cc[a]; }
+      sGeo[tid][6] = pid;
+      sGeo[tid][7] = (pid >= patch_begin && pid < patch_end) ? 1 : 0;
+    }
+    for (int idx = tid; idx < NA * NUV * S; idx += NT) sU[idx] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+      for (int a = 0; a < 3; ++a) {
+        int lo = 1 << 30, hi = 0;
+        for (int k = 0; k < NG; ++k) {
+          const Geom g = make_geom(cP, sGeo[k][6]);
+          lo = min(lo, g.lo[a] * n);
+          hi = max(hi, (a < DIM) ? (g.lo[a] + g.m[a]) * n : 0);
+        }
+        sUlo[a] = (a < DIM) ? lo : 0;
+        sUhi[a] = hi;
+      }
+    }
+    __syncthreads();
+    const int ulo[3] = {sUlo[0], sUlo[1], sUlo[2]}, uhi[3] = {sUhi[0], sUhi[1], sUhi[2]};
+    // scatter the members' phi onto the common box
+    for (int k = 0; k < NG; ++k) {
+      const Geom g = make_geom(cP, sGeo[k][6]);
+      const int ox = g.lo[0] * n - ulo[0], oy = g.lo[1] * n - ulo[1], oz = (DIM == 3) ? g.lo[2] * n - ulo[2] : 0;
+      for (int d = 0; d < S; ++d) {
+        const double *src = phi + ((size_t)sGeo[k][6] * S + d) * lay.nf_max;
+        double *dst = sU + (size_t)(k * S + d) * NUV * S;
+        for (int i = tid; i < g.Nf; i += NT) {
+          const int c = i % S;
+          int node = i / S;
+          const int ax = node % g.p[0];
+          node /= g.p[0];
+          const int ay = node % g.p[1], az = node / g.p[1];
+          dst[(((az + oz) * NU + (ay + oy)) * NU + (ax + ox)) * S + c] = src[i];
+        }
+      }
+    }
+    __syncthreads();
+    // neighbour cells of the group: [base - w, base + 1 + w] per axis
+    const int bx = sGeo[0][3], by = sGeo[0][4], bz = sGeo[0][5];  // member 0 = lowest corner of the 2^dim block
+    const int span = 2 * w + 2;
+    const int nq = (DIM == 3) ? span * span * span : span * span;
+    for (int qi = warp; qi < nq; qi += nwarp) {
+      int qc[3] = {bx - w + qi % span, by - w + (qi / span) % span, (DIM == 3) ? bz - w + qi / (span * span) : 0};
+      bool inside = true;
+#pragma unroll
+      for (int a = 0; a < DIM; ++a) inside = inside && (qc[a] >= 0 && qc[a] < cP.N);
+      if (!inside) continue;
+      const int qid = (int)morton_encode(qc, DIM, cP.ref);
+      const Geom gq = make_geom(cP, qid);
+      // sweep box = box(q) /\ common box, in global node coordinates
+      int b0[3], b1[3];
+      bool any = true;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (a < DIM) {
+          b0[a] = max(gq.lo[a] * n, ulo[a]);
+          b1[a] = min((gq.lo[a] + gq.m[a]) * n, uhi[a]);
+          if (b1[a] < b0[a]) any = false;
+        } else {
+          b0[a] = 0; b1[a] = 0;
+        }
+      }
+      const int ex = any ? b1[0] - b0[0] + 1 : 0, ey = b1[1] - b0[1] + 1, ez = b1[2] - b0[2] + 1;
+      const int sq_ = gq.p[0] * gq.p[1] * S;
+      for (int e = 0; e < S; ++e) {
+        double acc[NA];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+        const double *aq = aphi + ((size_t)qid * S + e) * lay.nf_max;
+        for (int t = lane; t < ex * ey; t += 32) {
+          const int iy = t / ex, ix = t - iy * ex;
+          const int gx = b0[0] + ix, gy = b0[1] + iy;
+          const double *q1 = aq + ((((b0[2] - gq.lo[2] * n)) * gq.p[1] + (gy - gq.lo[1] * n)) * gq.p[0] + (gx - gq.lo[0] * n)) * S;
+          const double *u1 = sU + (((b0[2] - ulo[2]) * NU + (gy - ulo[1])) * NU + (gx - ulo[0])) * S;
+          for (int iz = 0; iz < ez; ++iz) {
+#pragma unroll
+            for (int c = 0; c < S; ++c) {
+              const double v = q1[iz * sq_ + c];
+              const double *u = u1 + iz * NU * NU * S + c;
+#pragma unroll
+              for (int k = 0; k < NA; ++k) acc[k] += v * u[(size_t)k * NUV * S];
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NA; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane < NA) {
+          // lane k writes pair (member k / S, component k % S)
+          double val = 0.0;
+#pragma unroll
+          for (int k = 0; k < NA; ++k) val = (lane == k) ? acc[k] : val;
+          const int mem = lane / S, d = lane - mem * S;
+          if (sGeo[mem][7]) {
+            const int Dx = qc[0] - sGeo[mem][3], Dy = qc[1] - sGeo[mem][4], Dz = (DIM == 3) ? qc[2] - sGeo[mem][5] : 0;
+            if (abs(Dx) <= w && abs(Dy) <= w && abs(Dz) <= w) {
+              const int slot = (DIM == 3) ? ((Dz + w) * ww + (Dy + w)) * ww + (Dx + w) : (Dy + w) * ww + (Dx + w);
+              Kell[((size_t)sGeo[mem][6] * S + d) * cP.ell_width + slot * S + e] = val;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int DIM, int S>
+static cudaError_t launch_coarse_blocked_t(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi,
+                                           const double *aphi, double *Kell, const FinishLayout &lay, int NU) {
+  cudaError_t e = cudaFuncSetAttribute(k_coarse_blocked<DIM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // slots of neighbours outside the domain are never visited: clear the rows first
+  e = cudaMemsetAsync(Kell + (size_t)p0 * S * (lay.ell_width), 0, sizeof(double) * (size_t)(p1 - p0) * S * lay.ell_width, st);
+  if (e != cudaSuccess) return e;
+  k_coarse_blocked<DIM, S><<<grid, 512, smem, st>>>(p0, p1, phi, aphi, Kell, lay, NU);
+  return cudaGetLastError();
+}
+size_t coarse_blocked_smem(int dim, int s, int NU) {
+  size_t nuv = (dim == 3) ? (size_t)NU * NU * NU : (size_t)NU * NU;
+  return sizeof(double) * ((size_t)(1 << dim) * s * nuv * s);
+}
+cudaError_t launch_coarse_blocked(int dim, int s, int grid, size_t smem, cudaStream_t st, int p0, int p1,
+                                  const double *phi, const double *aphi, double *Kell, const FinishLayout &lay, int NU) {
+  if (dim == 3 && s == 1) return launch_coarse_blocked_t<3, 1>(grid, smem, st, p0, p1, phi, aphi, Kell, lay, NU);
+  if (dim == 2 && s == 1) return launch_coarse_blocked_t<2, 1>(grid, smem, st, p0, p1, phi, aphi, Kell, lay, NU);
+  if (dim == 2 && s == 2) return launch_coarse_blocked_t<2, 2>(grid, smem, st, p0, p1, phi, aphi, Kell, lay, NU);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,

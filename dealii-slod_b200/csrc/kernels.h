@@ -34,6 +34,7 @@ struct SelectLayout {
   long long m_stride;
 };
 struct FinishLayout {
+  int ell_width;
   int coef_doubles;
   int nf_max, ncd_max;
   int ldx;
@@ -93,6 +94,10 @@ cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const 
 cudaError_t launch_patch_finish(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                 const double *X, const double *cvec, double *phi, double *aphi,
                                 const FinishLayout &lay);
+// blocked coarse-matrix kernel: one CTA per Morton-aligned group of 2^dim patches, NU = nodes per axis of the common box
+size_t coarse_blocked_smem(int dim, int s, int NU);
+cudaError_t launch_coarse_blocked(int dim, int s, int grid, size_t smem, cudaStream_t st, int p0, int p1,
+                                  const double *phi, const double *aphi, double *Kell, const FinishLayout &lay, int NU);
 cudaError_t launch_gather(cudaStream_t st, const double *src, const long long *perm, double *dst, long long n);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);
