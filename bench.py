@@ -184,7 +184,7 @@ def run_reference(args, w, wname):
     line = {
         "impl": "reference", "metric": "slod_basis_patches_per_s", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(w, wname),
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} patches per step spread evenly over the {n_total(w)} patch ids; "
@@ -355,9 +355,15 @@ def main():
         kern["coarse"] = {"ms": float(kms[4])}
         dom = max(names, key=lambda nm: kms[names.index(nm)])
         achieved = kern[dom]["tflops"]
-        roofline = {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe on B200)", "kernel": "k_" + dom,
+        kname = {"patch_solve": "k_patch_solve_mma", "patch_dense": "k_patch_dense_mma",
+                 "patch_select": "k_select_fast + k_eig_tridiag/ql/finish", "patch_finish": "k_patch_finish"}[dom]
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")   # per-launch DRAM bytes from the committed ncu capture
+        if os.path.exists(tfile) and args.workload == DEFAULT_WORKLOAD and world == 1:
+            traffic = json.load(open(tfile)).get(kname)
+        roofline = {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe on B200)", "kernel": kname,
                     "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                    "traffic": None,
+                    "traffic": traffic,
                     "peak_source": "measured here by tools/fp64_peak.cu (MEASURED_PEAKS.json has no fp64 entry)",
                     "flop_model": "banded Cholesky Ni*bw^2 + 4*Ni*bw*Ncd per patch (SURVEY 8d), summed over actual patch shapes",
                     "kernels": kern}

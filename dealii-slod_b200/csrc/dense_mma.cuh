@@ -3,8 +3,8 @@
 // One CTA (NTILE warps) per patch.
 //  * M = P_i^T X / H^d is accumulated straight into a register tile (4 x NTILE/2 entries per thread) from a
 //    per-patch table of the interior X rows of every coarse cell;
-//  * M^{-1}: Gauss-Jordan sweeps on that register tile (like FullMatrix::gauss_jordan, source/LOD.cc:553); the
-//    pivot row / column travel through a double-buffered shared vector, one barrier per sweep;
+//  * M^{-1}: blocked Gauss-Jordan (8 x 8 pivot blocks) with DMMA tile updates in shared memory (replaces
+//    FullMatrix::gauss_jordan, source/LOD.cc:553);
 //  * BD and the Gram matrix use FP64 mma.sync tiles: warp w owns the coarse-column tile [8w, 8w+8) of BD and two
 //    tile rows (w and NTILE-1-w, lower triangle only) of G, whose accumulators stay in registers while the
 //    boundary rows stream through shared memory in tiles of 32.
@@ -122,86 +122,103 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       }
     }
     PH(1)
-    // ---- M^{-1}: Gauss-Jordan sweeps on the register tile ----
+    // ---- M^{-1}: blocked Gauss-Jordan (8 x 8 pivot blocks, no pivoting: M is SPD) with DMMA tile updates in
+    // shared memory; replaces FullMatrix::gauss_jordan (source/LOD.cc:553).  Step K:
+    //   Pinv = M_KK^{-1};  R_KJ = Pinv M_KJ;  M_IJ -= M_IK R_KJ (I, J != K);  M_IK = -M_IK Pinv;  M_KJ = R_KJ;  M_KK = Pinv.
+    // Warp w owns block row I = w.  The next pivot block is inverted by warp 0 while the others finish the column
+    // block, so a step costs three barriers.
     {
-      int badpiv = 0;
-      // One sweep = one uniform rank-1 update  m_ij <- a_ij - cl_i * rw_j  with a = m outside the pivot row/column
-      // and 0 on them, cl_k = -1, rw_k = 1/piv: this yields rw_j on the pivot row, -cl_i/piv on the pivot column and
-      // 1/piv at (k,k) without any per-entry case distinction.  The owner threads pick / clear their pivot row and
-      // column registers through warp-uniform switches (static register indices, no local memory, no selects).
-#define SLOD_ROW_CASE(I, BODY) case I: { constexpr int RI = I; BODY } break;
-#define SLOD_COL_CASE(J, BODY) case J: if (J < TW) { constexpr int CJ = (J < TW) ? J : 0; BODY } break;
-      for (int k = 0; k < ncd; ++k) {
-        const int kb = (k & 1) * NC;
-        const int ki = k & 3, kj = k >> 4;
-        const bool own_row = (ty == (k >> 2)), own_col = (tx == (k & 15));
-        if (own_row) {
-          switch (ki) {
-            SLOD_ROW_CASE(0, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
-            SLOD_ROW_CASE(1, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
-            SLOD_ROW_CASE(2, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
-            SLOD_ROW_CASE(3, _Pragma("unroll") for (int j = 0; j < TW; ++j) sPivRow[kb + tx + 16 * j] = m[RI][j];)
-          }
-        }
-        if (own_col) {
-          switch (kj) {
-            SLOD_COL_CASE(0, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(1, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(2, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(3, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(4, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(5, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(6, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-            SLOD_COL_CASE(7, _Pragma("unroll") for (int i = 0; i < 4; ++i) sPivCol[kb + r0 + i] = m[i][CJ];)
-          }
-        }
-        __syncthreads();
-        const double piv = sPivRow[kb + k];
-        if (!(piv > 0.0)) badpiv = 1;
-        const double ipiv = 1.0 / piv;
-        double rw[TW], cl[4];
-#pragma unroll
-        for (int j = 0; j < TW; ++j) rw[j] = sPivRow[kb + tx + 16 * j] * ipiv;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cl[i] = sPivCol[kb + r0 + i];
-        if (own_row) {
-          switch (ki) {
-            SLOD_ROW_CASE(0, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
-            SLOD_ROW_CASE(1, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
-            SLOD_ROW_CASE(2, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
-            SLOD_ROW_CASE(3, cl[RI] = -1.0; _Pragma("unroll") for (int j = 0; j < TW; ++j) m[RI][j] = 0.0;)
-          }
-        }
-        if (own_col) {
-          switch (kj) {
-            SLOD_COL_CASE(0, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(1, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(2, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(3, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(4, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(5, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(6, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-            SLOD_COL_CASE(7, rw[CJ] = ipiv; _Pragma("unroll") for (int i = 0; i < 4; ++i) m[i][CJ] = 0.0;)
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < TW; ++j) m[i][j] -= cl[i] * rw[j];
-      }
-#undef SLOD_ROW_CASE
-#undef SLOD_COL_CASE
-      if (badpiv && tid == 0) atomicOr(&status[pid], 2);
-      double *Mo = Minv_out + (size_t)w * lay.m_stride;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < TW; ++j) {
-          const int row = r0 + i, col = tx + 16 * j;
-          const bool in = row < ncd && col < ncd;
-          sM[row * LDM + col] = in ? m[i][j] : 0.0;
-          if (in) Mo[row * ncd + col] = m[i][j];
+        for (int j = 0; j < TW; ++j) sM[(r0 + i) * LDM + tx + 16 * j] = m[i][j];
+      __syncthreads();
+      int badpiv = 0;
+      const int nblk = (ncd + 7) >> 3;
+      double *sPinv = sPivRow;       // [64] current Pinv (row-major), the pivot vectors are not needed any more
+      double *sLi = sPivRow + 64;    // [64] scratch: L^{-1}
+      auto invert_pivot = [&](int K) {  // warp 0: Pinv = (L^{-1})^T L^{-1} of block K
+        const double2 pv = *reinterpret_cast<const double2 *>(sM + (8 * K + g) * LDM + 8 * K + 2 * t);
+        badpiv |= chol8_inv(pv.x, pv.y, lane, sLi);
+        double p0 = 0.0, p1 = 0.0;
+        const double f0 = sLi[t * 8 + g], f1 = sLi[(4 + t) * 8 + g];  // A[m][k] = Li[k][m] and B[k][n] = Li[k][n]
+        dmma884(p0, p1, f0, f0);
+        dmma884(p0, p1, f1, f1);
+        *reinterpret_cast<double2 *>(sPinv + g * 8 + 2 * t) = make_double2(p0, p1);
+      };
+      if (warp == 0) invert_pivot(0);
+      __syncthreads();
+      for (int K = 0; K < nblk; ++K) {
+        // ---- R_KJ = Pinv M_KJ, in place; NTILE - 1 tiles over the warps (warp J handles tile J) ----
+        if (warp != K && warp < nblk) {
+          const int J = warp;
+          double *ct = sM + (8 * K + g) * LDM + 8 * J + 2 * t;
+          const double b0 = sM[(8 * K + t) * LDM + 8 * J + g], b1 = sM[(8 * K + 4 + t) * LDM + 8 * J + g];
+          double r0_ = 0.0, r1_ = 0.0;
+          dmma884(r0_, r1_, sPinv[g * 8 + t], b0);
+          dmma884(r0_, r1_, sPinv[g * 8 + 4 + t], b1);
+          __syncwarp();
+          *reinterpret_cast<double2 *>(ct) = make_double2(r0_, r1_);
         }
+        __syncthreads();
+        // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments, sweeps J three tiles at a time ----
+        if (warp != K && warp < nblk) {
+          const int I = warp;
+          const double a0 = -sM[(8 * I + g) * LDM + 8 * K + t], a1 = -sM[(8 * I + g) * LDM + 8 * K + 4 + t];
+          for (int J0 = 0; J0 < nblk; J0 += 3) {
+            double2 c[3];
+            double b0[3], b1[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              int J = J0 + u;
+              if (J >= nblk || J == K) J = (K == 0) ? 1 : 0;   // dummy tile (not stored)
+              c[u] = *reinterpret_cast<const double2 *>(sM + (8 * I + g) * LDM + 8 * J + 2 * t);
+              b0[u] = sM[(8 * K + t) * LDM + 8 * J + g];
+              b1[u] = sM[(8 * K + 4 + t) * LDM + 8 * J + g];
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int J = J0 + u;
+              if (J < nblk && J != K) *reinterpret_cast<double2 *>(sM + (8 * I + g) * LDM + 8 * J + 2 * t) = c[u];
+            }
+          }
+        }
+        __syncthreads();
+        // ---- column block: M_IK = -M_IK Pinv (warp I), M_KK = Pinv (warp K); warp 0 inverts the next pivot first ----
+        double2 newcol = make_double2(0.0, 0.0);
+        if (warp < nblk) {
+          if (warp == K) {
+            newcol = *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
+          } else {
+            const int I = warp;
+            const double a0 = -sM[(8 * I + g) * LDM + 8 * K + t], a1 = -sM[(8 * I + g) * LDM + 8 * K + 4 + t];
+            dmma884(newcol.x, newcol.y, a0, sPinv[t * 8 + g]);
+            dmma884(newcol.x, newcol.y, a1, sPinv[(4 + t) * 8 + g]);
+          }
+        }
+        __syncthreads();   // every warp has read Pinv(K) and its old column tile
+        if (warp < nblk) *reinterpret_cast<double2 *>(sM + (8 * warp + g) * LDM + 8 * K + 2 * t) = newcol;
+        if (warp == 0 && K + 1 < nblk) {
+          // block (K+1, K+1) is final since the update above; warp 0's own column tile (row 0) is not part of it
+          invert_pivot(K + 1);
+        }
+        __syncthreads();
+      }
+      if (badpiv && lane == 0) atomicOr(&status[pid], 2);
+      double *Mo = Minv_out + (size_t)w * lay.m_stride;
+      for (int idx = tid; idx < ncd * NC; idx += NT) {
+        const int row = idx / NC, col = idx - row * NC;
+        if (col < ncd) {
+          Mo[row * ncd + col] = sM[row * LDM + col];
+        } else {
+          sM[row * LDM + col] = 0.0;   // padding columns / rows must not contribute to BD
+        }
+      }
+      for (int idx = tid; idx < (NC - ncd) * NC; idx += NT) sM[(ncd + idx / NC) * LDM + idx % NC] = 0.0;
     }
     PH(2)
     if (!geo.slod) continue;
@@ -250,20 +267,36 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
             count += __popc(mask);
           }
         }
+        for (int pos = count + lane; pos < kDNB; pos += 32) {  // padding: value 0 times X row 0
+          sAnbr[rb * kDNB + pos] = 0;
+          sArow[rb * kDNB + pos] = 0.0;
+        }
         if (lane == 0) sAcnt[rb] = count;
       }
       __syncthreads();
       PH(3)
-      // W tile = S_b X (zero padded to 32 x NC)
-      for (int idx = tid; idx < kDTB * NC; idx += NT) {
-        const int rb = idx / NC, col = idx % NC;
-        double acc = 0.0;
-        if (rb < nt && col < ncd) {
-          const int cnt = sAcnt[rb];
-#pragma unroll 8
-          for (int e = 0; e < cnt; ++e) acc += sArow[rb * kDNB + e] * X[(size_t)sAnbr[rb * kDNB + e] * lay.ldx + col];
+      // W tile = S_b X (zero padded to 32 x NC).  A thread owns one column and 8 boundary rows; the gathers of four
+      // rows are issued together (independent accumulators) so that four rounds of L2 latency overlap.
+      {
+        const int col = tid & (NC - 1), rbase = tid / NC;  // NT / NC = 4 rows per pass
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          int cmax = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cmax = max(cmax, sAcnt[rbase + 4 * (4 * half + u)]);
+          if (col >= ncd) cmax = 0;
+#pragma unroll 3
+          for (int e = 0; e < cmax; ++e) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rb = rbase + 4 * (4 * half + u);   // lists are zero padded: no predicate needed
+              acc[u] += sArow[rb * kDNB + e] * X[(size_t)sAnbr[rb * kDNB + e] * lay.ldx + col];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sT[(rbase + 4 * (4 * half + u)) * LDM + col] = acc[u];
         }
-        sT[rb * LDM + col] = acc;
       }
       __syncthreads();
       PH(4)
