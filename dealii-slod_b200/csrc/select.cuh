@@ -320,14 +320,15 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
             for (i = m - 1; i >= l; --i) {
               double f = sn * se[i];
               const double b = c * se[i];
-              r = sqrt(f * f + gg * gg);
+              const double h2 = f * f + gg * gg;
+              const double ir = rsqrt(h2);   // one MUFU-based op on the dependency chain instead of sqrt + divide
+              r = (h2 > 0.0) ? h2 * ir : 0.0;
               se[i + 1] = r;
               if (r == 0.0) {
                 sd[i + 1] -= p;
                 se[m] = 0.0;
                 break;
               }
-              const double ir = 1.0 / r;
               sn = f * ir;
               c = gg * ir;
               gg = sd[i + 1] - p;

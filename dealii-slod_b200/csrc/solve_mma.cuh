@@ -311,9 +311,9 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       // The warps that share warp 0's scheduler hold their DMMAs back until the factorisation chain is through:
       // its dependent fp64 operations would otherwise queue behind them on the shared fp64 pipe.
       if ((warp & 3) == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * (NW / 4)) : "memory");
-      if (warp & 3) {
-        // the other tiles go round robin over the warps of the three schedulers warp 0 does not sit on (its
-        // fp64 dependency chain shares the pipe with their DMMAs), three at a time for instruction-level parallelism
+      // the other tiles go round robin over the warps of the three schedulers warp 0 does not sit on (its fp64
+      // dependency chain shares the pipe with their DMMAs), three at a time for instruction-level parallelism
+      auto do_trailing = [&]() {
         constexpr int NTW = NW - NW / 4;
         const int wrank = warp - 1 - (warp >> 2);  // 0 .. NTW-1
         for (int tt = 1 + wrank; tt < ntile; tt += 3 * NTW) {
@@ -343,18 +343,31 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           for (int u = 0; u < 3; ++u)
             if (tt + u * NTW < ntile) *reinterpret_cast<double2 *>(ct[u]) = c[u];
         }
+      };
+      auto do_rhs = [&]() {
+#pragma unroll
+        for (int off = 1; off < RBMAX; ++off) {
+          if (off <= nl) {
+            int sI = kslot + off;
+            if (sI >= RB) sI -= RB;
+            const double a0 = sLpT[t * LDP + 8 * sI + g], a1 = sLpT[(4 + t) * LDP + 8 * sI + g];
+            dmma884(cr[off][0], cr[off][1], a0, yb0);
+            dmma884(cr[off][0], cr[off][1], a1, yb1);
+          }
+        }
+      };
+      // Skew: on each scheduler half of the warps run the (latency-bound) trailing tiles first and the (DMMA-bound)
+      // right-hand-side update second, the other half the other way round, so that the two overlap on the fp64 pipe.
+      if ((warp & 3) == 0) {
+        do_rhs();
+      } else if ((warp >> 2) & 1) {
+        do_rhs();
+        do_trailing();
+      } else {
+        do_trailing();
+        do_rhs();
       }
       PH(3)
-#pragma unroll
-      for (int off = 1; off < RBMAX; ++off) {
-        if (off <= nl) {
-          int sI = kslot + off;
-          if (sI >= RB) sI -= RB;
-          const double a0 = sLpT[t * LDP + 8 * sI + g], a1 = sLpT[(4 + t) * LDP + 8 * sI + g];
-          dmma884(cr[off][0], cr[off][1], a0, yb0);
-          dmma884(cr[off][0], cr[off][1], a1, yb1);
-        }
-      }
       PH(4)
       // ---- slide: block k + RB takes the slot of block k; the register window moves up by one ----
       double n0 = 0.0, n1 = 0.0;
