@@ -51,7 +51,10 @@ struct slod_ctx {
   // chunk workspaces
   int chunk = 0;
   int *d_ids = nullptr;
-  double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr;
+  double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr, *d_W = nullptr;
+  FluxLayout xl{};
+  size_t smem_flux = 0;
+  int grid_flux = 0;
   int solve_grid = 0;
   int dense_ntile = 0;   // 0: generic SIMT dense stage, else tensor-core variant
   int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
@@ -243,7 +246,7 @@ void free_dev(slod_ctx *c) {
     p = nullptr;
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
-  F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws);
+  F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
   F(c->d_perm); F(c->d_val);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
 }
@@ -302,7 +305,8 @@ int prepare_coefficients(slod_ctx *ctx) {
 int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   const Params &P = ctx->P;
   if (ctx->chunk > 0) return SLOD_OK;
-  const size_t per_patch = ((size_t)ctx->sl.x_stride + 2 * (size_t)ctx->dl.m_stride + (size_t)P.s * P.NcdMax) * 8 + 4;
+  const size_t per_patch = ((size_t)ctx->sl.x_stride + 2 * (size_t)ctx->dl.m_stride + (size_t)P.s * P.NcdMax +
+                            (ctx->dense_ntile ? (size_t)ctx->xl.w_stride : 0)) * 8 + 4;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
@@ -316,6 +320,7 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
   CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
   CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
+  if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
   CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
   // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
   {
@@ -383,9 +388,14 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
       CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Lws, ctx->d_status, ctx->sl));
     CK(cudaEventRecord(ctx->ev[1], st));
-    if (ctx->dense_ntile)
+    if (ctx->dense_ntile) {
+      CK(launch_patch_flux(std::min(nw, ctx->grid_flux), ctx->smem_flux, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+                           ctx->d_W, ctx->xl));
       CK(launch_patch_dense_mma(ctx->dense_ntile, std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw,
-                                ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+                                ctx->d_coef, ctx->d_X, ctx->d_W, ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status,
+                                ctx->dl));
+      ctx->launches += 1;
+    }
     else
       CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
@@ -679,6 +689,13 @@ int slod_create(const slod_params *par, slod_ctx **out) {
       }
     }
   }
+  if (ctx->dense_ntile) {
+    FluxLayout &xl = ctx->xl;
+    xl.coef_doubles = coef_doubles; xl.ldx = sl.ldx; xl.nb_max = nb_max; xl.x_stride = sl.x_stride;
+    xl.w_stride = (long long)((nb_max + 31) / 32 * 32) * sl.ldx;
+    dl.w_stride = xl.w_stride;
+    ctx->smem_flux = flux_smem(coef_doubles, sl.ldx, nb_max);
+  }
   SelectPlan &sp = ctx->sp;
   sp.s = P.s;
   sp.lay.threads = big ? 512 : 128;
@@ -732,6 +749,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   sp.grid_fin = ctx->n_sm * per_sm(sp.smem_fin, 128);
   sp.grid_ql = ctx->n_sm * 8;
   ctx->grid_finish = ctx->n_sm * per_sm(ctx->smem_finish, 256);
+  ctx->grid_flux = ctx->n_sm * std::min(4, per_sm(ctx->smem_flux, 256));
   ctx->grid_coarse = ctx->n_sm * per_sm(ctx->smem_coarse, 256);
 
   auto cuda_bad = [&](const char *what, cudaError_t e) {
@@ -1111,9 +1129,11 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
                               ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw));
   else
     CK(launch_patch_solve(1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl));
-  if (ctx->dense_ntile)
-    CK(launch_patch_dense_mma(ctx->dense_ntile, 1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv,
-                              ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+  if (ctx->dense_ntile) {
+    CK(launch_patch_flux(1, ctx->smem_flux, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_W, ctx->xl));
+    CK(launch_patch_dense_mma(ctx->dense_ntile, 1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_W,
+                              ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
+  }
   else
     CK(launch_patch_dense(1, ctx->smem_dense, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Minv, ctx->d_G, ctx->d_diag,
                           ctx->d_status, ctx->dl));

@@ -14,13 +14,12 @@
 namespace slod {
 
 constexpr int kDTB = 32;    // boundary rows per tile
-constexpr int kDNB = 56;    // stencil slots reserved per boundary row (27 * spacedim <= 54)
 
 template <int NTILE>
 __global__ void __launch_bounds__(32 * NTILE, 1)
 k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
-                  const double *__restrict__ Xbuf, double *__restrict__ Minv_out, double *__restrict__ G_out,
-                  double *__restrict__ diag, int *__restrict__ status, DenseLayout lay) {
+                  const double *__restrict__ Xbuf, const double *__restrict__ Wbuf, double *__restrict__ Minv_out,
+                  double *__restrict__ G_out, double *__restrict__ diag, int *__restrict__ status, DenseLayout lay) {
   constexpr int NT = 32 * NTILE;
   constexpr int NC = 8 * NTILE;   // padded coarse dimension
   constexpr int LDM = NC + 4;     // LDM % 16 == 4 : conflict-free fragment loads
@@ -32,12 +31,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   double *sT = sM + NC * LDM;             // [kDTB][LDM] W tile, then BD tile
   double *sPivRow = sT + kDTB * LDM;      // [2][NC]
   double *sPivCol = sPivRow + 2 * NC;     // [2][NC]
-  double *sArow = sPivCol + 2 * NC;       // [kDTB][kDNB] compact stencil values of the boundary rows
-  int *sAnbr = (int *)(sArow + kDTB * kDNB);  // [kDTB][kDNB] interior dof of each compact entry
-  int *sAcnt = sAnbr + kDTB * kDNB;           // [kDTB]
-  int *sMList = sAcnt + kDTB;                 // [NC][28] X rows of each coarse row: (xrow << 2 | log2 weight), count first
-  int *sBlist = sMList + NC * 28;             // [nb_max] boundary dofs
-  __shared__ int sNb;
+  int *sMList = (int *)(sPivCol + 2 * NC);  // [NC][28] X rows of each coarse row: (xrow << 2 | log2 weight), count first
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ty = tid >> 4, tx = tid & 15;
@@ -51,7 +45,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
     PH_DECL
     load_coef(geo, d_coef, sCoef);
-    if (tid == 0) sNb = 0;
     // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row ----
     {
       const int npc = cP.n + 1;
@@ -74,25 +67,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         }
         sMList[row * 28] = cnt;
       }
-    }
-    if (geo.slod && tid < 32) {  // boundary dofs, ascending
-      int count = 0;
-      for (int base = 0; base < geo.nnodes; base += 32) {
-        const int node = base + tid;
-        bool isb = false;
-        if (node < geo.nnodes) {
-          int a[3];
-          node_coords(geo, node, a);
-          isb = (node_class(cP, geo, a) & 1) != 0;
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, isb);
-        if (isb) {
-          const int pos = (count + __popc(mask & ((1u << tid) - 1u))) * s;
-          for (int c = 0; c < s; ++c) sBlist[pos + c] = node * s + c;
-        }
-        count += __popc(mask);
-      }
-      if (tid == 0) sNb = count * s;
     }
     __syncthreads();
 
@@ -149,6 +123,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       if (warp == 0) invert_pivot(0);
       __syncthreads();
       for (int K = 0; K < nblk; ++K) {
+        PH(2)
         // ---- R_KJ = Pinv M_KJ, in place; NTILE - 1 tiles over the warps (warp J handles tile J) ----
         if (warp != K && warp < nblk) {
           const int J = warp;
@@ -161,6 +136,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           *reinterpret_cast<double2 *>(ct) = make_double2(r0_, r1_);
         }
         __syncthreads();
+        PH(9)
         // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments, sweeps J three tiles at a time ----
         if (warp != K && warp < nblk) {
           const int I = warp;
@@ -188,6 +164,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           }
         }
         __syncthreads();
+        PH(10)
         // ---- column block: M_IK = -M_IK Pinv (warp I), M_KK = Pinv (warp K); warp 0 inverts the next pivot first ----
         double2 newcol = make_double2(0.0, 0.0);
         if (warp < nblk) {
@@ -207,6 +184,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           invert_pivot(K + 1);
         }
         __syncthreads();
+        PH(11)
       }
       if (badpiv && lane == 0) atomicOr(&status[pid], 2);
       double *Mo = Minv_out + (size_t)w * lay.m_stride;
@@ -228,101 +206,33 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     double gacc[NTILE + 1][2];
 #pragma unroll
     for (int e = 0; e <= NTILE; ++e) gacc[e][0] = gacc[e][1] = 0.0;
-    const int nbd = sNb;
-    const int nst = (cP.dim == 3) ? 27 : 9;
-    const int per_row = nst * s;
+    int nbd = 0;   // patch-boundary dofs (id 99): nodes on a patch side that is not part of the domain boundary
+    {
+      int cnt_all = 1, cnt_nob = 1;
+      for (int a = 0; a < cP.dim; ++a) {
+        cnt_all *= geo.p[a];
+        cnt_nob *= geo.p[a] - (geo.domlo[a] ? 0 : 1) - (geo.domhi[a] ? 0 : 1);
+      }
+      nbd = s * (cnt_all - cnt_nob);
+    }
     const int ksteps = (ncd + 3) >> 2;
     const int I1 = warp, I2 = NTILE - 1 - warp;
-    const int lgn = __ffs(cP.n) - 1;
+    // W = S_b X - P_b comes from k_patch_flux, zero padded to whole tiles; a thread moves 8 doubles of each tile
+    // (NT * 8 = 32 * NC) and holds the next tile in registers while the tensor phases of the current one run.
+    const double *Wp = Wbuf + (size_t)w * lay.w_stride;
+    const int wrow = tid / (NC / 8), wcol = 8 * (tid % (NC / 8));
+    double2 wreg[4];
+    auto load_w = [&](int t0) {
+      const double2 *src = reinterpret_cast<const double2 *>(Wp + (size_t)(t0 + wrow) * NC + wcol);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wreg[q] = src[q];
+    };
+    if (nbd > 0) load_w(0);
     for (int t0 = 0; t0 < nbd; t0 += kDTB) {
-      const int nt = min(kDTB, nbd - t0);
-      // compact stencil rows: one warp per boundary row, ballot compaction keeps the slot order
-      for (int rb = warp; rb < kDTB; rb += NTILE) {
-        int count = 0;
-        if (rb < nt) {
-          const int dof = sBlist[t0 + rb];
-          int a[3];
-          node_coords(geo, dof / s, a);
-          for (int base = 0; base < per_row; base += 32) {
-            const int slot = base + lane;
-            bool ok = slot < per_row;
-            int nbr = 0;
-            double val = 0.0;
-            if (ok) {
-              const int cb = slot % s, e = slot / s;
-              int dl[3] = {e % 3 - 1, (e / 3) % 3 - 1, (cP.dim == 3) ? (e / 9 - 1) : 0};
-              int b[3] = {a[0] + dl[0], a[1] + dl[1], a[2] + dl[2]};
-              _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) ok = ok && (b[x] >= 1 && b[x] <= geo.p[x] - 2);
-              if (ok) {
-                nbr = interior_index(geo, b) * s + cb;
-                val = stiff_entry(cP, geo, sCoef, a, dl, dof % s, cb);
-              }
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-              const int pos = count + __popc(mask & ((1u << lane) - 1u));
-              sAnbr[rb * kDNB + pos] = nbr;
-              sArow[rb * kDNB + pos] = val;
-            }
-            count += __popc(mask);
-          }
-        }
-        for (int pos = count + lane; pos < kDNB; pos += 32) {  // padding: value 0 times X row 0
-          sAnbr[rb * kDNB + pos] = 0;
-          sArow[rb * kDNB + pos] = 0.0;
-        }
-        if (lane == 0) sAcnt[rb] = count;
-      }
-      __syncthreads();
       PH(3)
-      // W tile = S_b X (zero padded to 32 x NC).  A thread owns one column and 8 boundary rows; the gathers of four
-      // rows are issued together (independent accumulators) so that four rounds of L2 latency overlap.
-      {
-        const int col = tid & (NC - 1), rbase = tid / NC;  // NT / NC = 4 rows per pass
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          double acc[4] = {0.0, 0.0, 0.0, 0.0};
-          int cmax = 0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) cmax = max(cmax, sAcnt[rbase + 4 * (4 * half + u)]);
-          if (col >= ncd) cmax = 0;
-#pragma unroll 3
-          for (int e = 0; e < cmax; ++e) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int rb = rbase + 4 * (4 * half + u);   // lists are zero padded: no predicate needed
-              acc[u] += sArow[rb * kDNB + e] * X[(size_t)sAnbr[rb * kDNB + e] * lay.ldx + col];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) sT[(rbase + 4 * (4 * half + u)) * LDM + col] = acc[u];
-        }
-      }
-      __syncthreads();
-      PH(4)
-      // ... - P_b : every boundary dof lies in at most 2^dim coarse cells
-      for (int idx = tid; idx < nt * 8; idx += NT) {
-        const int rb = idx >> 3, corner = idx & 7;
-        if (corner >= (1 << cP.dim)) continue;
-        const int dof = sBlist[t0 + rb];
-        int a[3];
-        node_coords(geo, dof / s, a);
-        int kc[3] = {0, 0, 0};
-        double wgt = cP.pw;
-        bool ok = true;
-        _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim) {
-          const int q = a[x] >> lgn, rem = a[x] - (q << lgn);
-          if ((corner >> x) & 1) {
-            if (rem != 0 || q < 1) ok = false;
-            kc[x] = q - 1;
-          } else {
-            if (q > geo.m[x] - 1) ok = false;
-            kc[x] = q;
-            if (rem != 0) wgt *= 2.0;
-          }
-        }
-        if (ok) sT[rb * LDM + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
-      }
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(sT + wrow * LDM + wcol + 2 * q) = wreg[q];
+      if (t0 + kDTB < nbd) load_w(t0 + kDTB);
       __syncthreads();
       PH(5)
       // BD tile = W tile * Minv : warp owns 8 columns, 4 row tiles
@@ -352,6 +262,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           dmma884(gacc[e][0], gacc[e][1], first ? a1 : a2, rowp[8 * J]);
         }
       }
+      __syncthreads();   // the next tile overwrites sT
       PH(7)
     }
     {

@@ -471,6 +471,7 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
 }
 
 }  // namespace slod
+#include "flux.cuh"
 #include "dense_mma.cuh"
 namespace slod {
 
@@ -867,27 +868,39 @@ cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int
 }
 template <int NTILE>
 static cudaError_t launch_dense_t(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                                  const double *X, double *Minv, double *G, double *diag, int *status,
+                                  const double *X, const double *W, double *Minv, double *G, double *diag, int *status,
                                   const DenseLayout &lay) {
   cudaError_t e = cudaFuncSetAttribute(k_patch_dense_mma<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_patch_dense_mma<NTILE><<<grid, 32 * NTILE, smem, st>>>(ids, n_work, coef, X, Minv, G, diag, status, lay);
+  k_patch_dense_mma<NTILE><<<grid, 32 * NTILE, smem, st>>>(ids, n_work, coef, X, W, Minv, G, diag, status, lay);
   return cudaGetLastError();
 }
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
+  (void)nb_max;
   const int NC = 8 * ntile, LDM = NC + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 4 * NC + kDTB * kDNB) +
-         sizeof(int) * ((size_t)kDTB * kDNB + kDTB + NC * 28 + nb_max + 8);
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 4 * NC) +
+         sizeof(int) * ((size_t)NC * 28 + 8);
 }
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
-                                   const double *coef, const double *X, double *Minv, double *G, double *diag,
-                                   int *status, const DenseLayout &lay) {
+                                   const double *coef, const double *X, const double *W, double *Minv, double *G,
+                                   double *diag, int *status, const DenseLayout &lay) {
   switch (ntile) {
-    case 4: return launch_dense_t<4>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
-    case 8: return launch_dense_t<8>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
-    case 16: return launch_dense_t<16>(grid, smem, st, ids, n_work, coef, X, Minv, G, diag, status, lay);
+    case 4: return launch_dense_t<4>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
+    case 8: return launch_dense_t<8>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
+    case 16: return launch_dense_t<16>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
   }
   return cudaErrorInvalidValue;
+}
+size_t flux_smem(int coef_doubles, int ldx, int nb_max) {
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)kFTB * (ldx + 4) + (size_t)kFTB * kFNB) +
+         sizeof(int) * ((size_t)kFTB * kFNB + kFTB + nb_max + 8);
+}
+cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                              const double *X, double *W, const FluxLayout &lay) {
+  cudaError_t e = cudaFuncSetAttribute(k_patch_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_patch_flux<<<grid, 256, smem, st>>>(ids, n_work, coef, X, W, lay);
+  return cudaGetLastError();
 }
 
 size_t select_fast_smem(int ncd_max) {

@@ -20,12 +20,20 @@ struct SolveLayout {
   long long lws_per_cta;  // doubles of L workspace per CTA
 };
 struct DenseLayout {
+  long long w_stride;  // doubles per patch in the flux buffer W
   int threads;
   int ncd_max, nb_max;
   int coef_doubles;
   int ldx;
   long long x_stride;
   long long m_stride;  // ncd_max^2
+};
+struct FluxLayout {
+  int coef_doubles;
+  int ldx;             // padded coarse columns (leading dimension of X and W rows)
+  int nb_max;
+  long long x_stride;
+  long long w_stride;  // doubles per patch in Wbuf: round_up(nb_max, 32) * ldx
 };
 struct SelectLayout {
   int threads;
@@ -53,11 +61,15 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);
+// boundary flux W = S_b X - P_b for the tensor-core dense stage
+size_t flux_smem(int coef_doubles, int ldx, int nb_max);
+cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                              const double *X, double *W, const FluxLayout &lay);
 // tensor-core dense stage, ntile in {4, 8, 16} (8*ntile >= coarse dofs per patch)
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max);
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
-                                   const double *coef, const double *X, double *Minv, double *G, double *diag,
-                                   int *status, const DenseLayout &lay);
+                                   const double *coef, const double *X, const double *W, double *Minv, double *G,
+                                   double *diag, int *status, const DenseLayout &lay);
 // selection pipeline (select.cuh): fast path -> tridiagonalisation + QL (rotation log) -> Jacobi fallback
 struct EigLayout {
   int nmax, ldh;
