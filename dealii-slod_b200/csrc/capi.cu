@@ -309,7 +309,7 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
                             (ctx->dense_ntile ? (size_t)ctx->xl.w_stride : 0)) * 8 + 4;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = std::min<size_t>(free_b / 3, (size_t)24 << 30);
+  size_t budget = std::min<size_t>(free_b / 2, (size_t)96 << 30);   // one chunk for 2^15 3-D patches (53 GB) on a 180 GB part
   int64_t chunk = std::max<int64_t>(1, (int64_t)(budget / per_patch));
   (void)n_range;
   chunk = std::min<int64_t>(chunk, ctx->n_patches);
