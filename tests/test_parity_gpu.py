@@ -64,6 +64,9 @@ CASES = [
     dict(dim=2, s=2, ref=3, n=2, ell=1),                             # cfg 3 shape (elasticity)
     dict(dim=2, s=2, ref=4, n=2, ell=2, sample=40),
     dict(dim=2, s=1, ref=4, n=2, ell=2, kind="binary1e4", seed=1235),  # high contrast
+    dict(dim=2, s=1, ref=3, n=2, ell=0),                             # oversampling 0: one-cell patches -> LOD (source/LOD.cc:563)
+    dict(dim=2, s=1, ref=1, n=2, ell=1),                             # 2 x 2 cells: smallest mesh with more than one patch
+    dict(dim=3, s=1, ref=1, n=2, ell=1),
     dict(dim=3, s=1, ref=2, n=2, ell=1),
     dict(dim=3, s=1, ref=3, n=2, ell=2, sample=10, kind="uniform1e4", seed=3001),   # cfg 4 shape
 ]
