@@ -316,34 +316,40 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
             double r = sqrt(gg * gg + 1.0);
             gg = sd[m] - sd[l] + se[l] / (gg + copysign(r, gg));
             double sn = 1.0, c = 1.0, p = 0.0;
-            int i;
-            for (i = m - 1; i >= l; --i) {
-              double f = sn * se[i];
-              const double b = c * se[i];
+            int i = m - 1;
+            // operands of rotation i travel in registers: the next ones are fetched one rotation ahead, and what
+            // rotation i + 1 produced for position i + 1 is handed over instead of going through shared memory
+            double e_i = se[i], d_lo = sd[i], d_hi = sd[i + 1], gh_lo = sgh[i], gh_hi = sgh[i + 1];
+            for (; i >= l; --i) {
+              double e_n = 0.0, d_n = 0.0, gh_n = 0.0;
+              if (i > l) { e_n = se[i - 1]; d_n = sd[i - 1]; gh_n = sgh[i - 1]; }
+              const double f = sn * e_i;
+              const double b = c * e_i;
               const double h2 = f * f + gg * gg;
               const double ir = rsqrt(h2);   // one MUFU-based op on the dependency chain instead of sqrt + divide
               r = (h2 > 0.0) ? h2 * ir : 0.0;
               se[i + 1] = r;
               if (r == 0.0) {
-                sd[i + 1] -= p;
+                sd[i + 1] = d_hi - p;
                 se[m] = 0.0;
                 break;
               }
               sn = f * ir;
               c = gg * ir;
-              gg = sd[i + 1] - p;
-              r = (sd[i] - gg) * sn + 2.0 * c * b;
+              gg = d_hi - p;
+              r = (d_lo - gg) * sn + 2.0 * c * b;
               p = sn * r;
               sd[i + 1] = gg + p;
               gg = c * r - b;
               // Z <- Z R : columns (i, i+1); here applied as x <- R^T x to g_h
-              f = sgh[i + 1];
-              sgh[i + 1] = sn * sgh[i] + c * f;
-              sgh[i] = c * sgh[i] - sn * f;
+              sgh[i + 1] = sn * gh_lo + c * gh_hi;
+              gh_hi = c * gh_lo - sn * gh_hi;
               cs[nrot] = make_double2(c, sn);
               ri[nrot] = (unsigned short)i;
               ++nrot;
+              e_i = e_n; d_hi = d_lo; d_lo = d_n; gh_lo = gh_n;
             }
+            sgh[i + 1] = gh_hi;   // position l after a full sweep, position i + 1 after an early exit
             if (r == 0.0 && i >= l) continue;
             sd[l] -= p;
             se[l] = gg;

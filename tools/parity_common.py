@@ -69,7 +69,14 @@ def margin_safe(info, d):
     """False when a discontinuous decision of the reference rule is within rounding of flipping."""
     if not info.get("slod", False):
         return True
-    return abs(info["dinf"][d] - 0.5) > 1e-3
+    if abs(info["dinf"][d] - 0.5) <= 1e-3:
+        return False
+    # the singular-value threshold 1e-15 * sigma_0 (source/LOD.cc:667): a singular value of size ~eps * sigma_0 is
+    # only known to O(1) relative accuracy, so a ratio within two decades of the threshold can fall on either side
+    # (LAPACK's dgesdd included) and the selected d changes completely
+    sig = np.asarray(info["sigma"][d])
+    ratio = sig / sig[0]
+    return not np.any((ratio > 1e-17) & (ratio < 1e-13))
 
 
 def selection_from_G(G, Minv, X, d, s_dim=None):
