@@ -296,7 +296,10 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
     __syncwarp();
     for (int i = lane; i < n; i += 32) { sd[i] = V[i]; se[i] = V[nmax + i]; sgh[i] = V[3 * nmax + i]; }
     __syncwarp();
-    if (lane == 0) {
+    // Every lane runs the (identical) scalar recurrence -- same shared-memory addresses, same values, so control flow
+    // stays warp uniform and the fp64 pipe sees the same instruction count as with one active lane -- which lets the
+    // warp scan for the next negligible off-diagonal 32 entries at a time.  Lane 0 alone writes the rotation log.
+    {
       double2 *cs = rot_cs + (size_t)item * lay.log_cap;
       unsigned short *ri = rot_i + (size_t)item * lay.log_cap;
       long long nrot = 0;
@@ -305,16 +308,21 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
       for (int l = 0; l < n && !fail; ++l) {
         int iter = 0, m;
         do {
-          for (m = l; m < n - 1; ++m) {
-            const double dd = fabs(sd[m]) + fabs(sd[m + 1]);
-            if (fabs(se[m]) <= 2.220446049250313e-16 * dd) break;
+          m = n - 1;
+          for (int m0 = l; m0 < n - 1; m0 += 32) {
+            const int mm = m0 + lane;
+            bool small = false;
+            if (mm < n - 1) small = fabs(se[mm]) <= 2.220446049250313e-16 * (fabs(sd[mm]) + fabs(sd[mm + 1]));
+            const unsigned hit = __ballot_sync(0xffffffffu, small);
+            if (hit) { m = m0 + __ffs(hit) - 1; break; }
           }
           if (m != l) {
             if (++iter > 60 || nrot + (m - l) > lay.log_cap) { fail = true; break; }
             ++total_iter;
-            double gg = (sd[l + 1] - sd[l]) / (2.0 * se[l]);
+            const double d_l = sd[l];   // kept in a register: every lane executes this code, no read-modify-write on shared memory
+            double gg = (sd[l + 1] - d_l) / (2.0 * se[l]);
             double r = sqrt(gg * gg + 1.0);
-            gg = sd[m] - sd[l] + se[l] / (gg + copysign(r, gg));
+            gg = sd[m] - d_l + se[l] / (gg + copysign(r, gg));
             double sn = 1.0, c = 1.0, p = 0.0;
             int i = m - 1;
             // operands of rotation i travel in registers: the next ones are fetched one rotation ahead, and what
@@ -344,21 +352,25 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
               // Z <- Z R : columns (i, i+1); here applied as x <- R^T x to g_h
               sgh[i + 1] = sn * gh_lo + c * gh_hi;
               gh_hi = c * gh_lo - sn * gh_hi;
-              cs[nrot] = make_double2(c, sn);
-              ri[nrot] = (unsigned short)i;
+              if (lane == 0) {
+                cs[nrot] = make_double2(c, sn);
+                ri[nrot] = (unsigned short)i;
+              }
               ++nrot;
               e_i = e_n; d_hi = d_lo; d_lo = d_n; gh_lo = gh_n;
             }
             sgh[i + 1] = gh_hi;   // position l after a full sweep, position i + 1 after an early exit
             if (r == 0.0 && i >= l) continue;
-            sd[l] -= p;
+            sd[l] = d_l - p;
             se[l] = gg;
             se[m] = 0.0;
           }
         } while (m != l);
       }
-      rot_n[2 * item] = fail ? -1 : (int)nrot;
-      rot_n[2 * item + 1] = total_iter;
+      if (lane == 0) {
+        rot_n[2 * item] = fail ? -1 : (int)nrot;
+        rot_n[2 * item + 1] = total_iter;
+      }
     }
     __syncwarp();
     for (int i = lane; i < n; i += 32) { V[4 * nmax + i] = sd[i]; V[5 * nmax + i] = sgh[i]; }
