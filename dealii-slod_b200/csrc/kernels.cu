@@ -904,7 +904,8 @@ cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int 
 }
 
 size_t select_fast_smem(int ncd_max) {
-  return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + 4 * (size_t)ncd_max);
+  const size_t nbk = (size_t)(ncd_max + 6) / 8;
+  return sizeof(double) * (nbk * (nbk + 1) / 2 * 64 + 8 * nbk + 8);
 }
 size_t select_jacobi_smem(int ncd_max) {
   return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + (size_t)ncd_max * ncd_max + 6 * (size_t)ncd_max) +

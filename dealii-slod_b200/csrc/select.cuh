@@ -27,20 +27,25 @@ __device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 
 // ------------------------------------------------------------------------------------------------
 // k_select_fast
 // ------------------------------------------------------------------------------------------------
+// 8 x 8 tiles of the packed lower triangle: tile (I, J), I >= J, at tri(I) + J; inside a tile element (r, c) sits at
+// r * 8 + (c ^ 4 * ((r >> 1) & 1)): A-fragment, transposed-B-fragment and C-fragment accesses are bank-conflict free.
+__device__ __forceinline__ int tile_off(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
+__device__ __forceinline__ int tile_el(int r, int c) { return r * 8 + (c ^ (((r >> 1) & 1) << 2)); }
+
 __global__ void __launch_bounds__(256, 3)
 k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ Minv_in,
               const double *__restrict__ G_in, double *__restrict__ cvec, double *__restrict__ diag,
               int *__restrict__ counters, int *__restrict__ work_list, int list_slot, SelectLayout lay) {
   extern __shared__ double smem[];
   const int nmax = lay.ncd_max;
-  double *Lc = smem;                                   // packed lower triangle, row i at i (i + 1) / 2
-  double *sg = Lc + (size_t)nmax * (nmax + 1) / 2;     // g
-  double *sd = sg + nmax;                              // d
-  double *slam = sd + nmax;                            // sqrt of the pivots
-  double *scol = slam + nmax;                          // scaled pivot column
+  const int nbk_max = (nmax + 6) >> 3;                    // blocks of 8 covering n = ncd - 1 <= nmax - 1
+  double *sL = smem;                                      // tiles of the lower triangle (Cholesky in place)
+  double *sz = sL + (size_t)nbk_max * (nbk_max + 1) / 2 * 64;   // [8 nbk_max] right-hand side -> solution
   __shared__ int sFlag;
   __shared__ int sWork;
+  __shared__ double sStat[4];
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NWARP = NT >> 5;
+  const int g = lane >> 2, t = lane & 3;
   for (;;) {
     __syncthreads();
     if (tid == 0) sWork = atomicAdd(&counters[0], 1);
@@ -48,15 +53,15 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
     const int w = sWork;
     if (w >= n_work) break;
     const int pid = patch_ids[w];
-    const Geom g = make_geom(cP, pid);
-    const int ncd = g.Ncd, s = cP.s;
+    const Geom geo = make_geom(cP, pid);
+    const int ncd = geo.Ncd, s = cP.s;
     const double *Minv = Minv_in + (size_t)w * lay.m_stride;
     const double *Gf = G_in + (size_t)w * lay.m_stride;
     for (int d = 0; d < s; ++d) {
       double *cv = cvec + ((size_t)w * s + d) * lay.ncd_max;
       double *dg = diag + ((size_t)pid * s + d) * 8;
       __syncthreads();
-      if (!g.slod) {  // LOD branch: c = M^{-1} e_d (source/LOD.cc:570-593)
+      if (!geo.slod) {  // LOD branch: c = M^{-1} e_d (source/LOD.cc:570-593)
         for (int i = tid; i < ncd; i += NT) cv[i] = Minv[i * ncd + d];
         if (tid == 0) { dg[0] = 0; dg[1] = 0; dg[2] = 0; dg[3] = 0; dg[5] = 0; dg[6] = 0; }
         continue;
@@ -64,56 +69,135 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
       const int n = ncd - 1;  // considered_candidates: all coarse dofs but d (source/LOD.cc:637-640)
       bool done = false;
       if (lay.fast_path) {
-        for (int i = warp; i < n; i += NWARP) {
-          const double *grow = Gf + (size_t)(i + (i >= d)) * ncd;
-          for (int j = lane; j <= i; j += 32) Lc[i * (i + 1) / 2 + j] = grow[j + (j >= d)];
+        // ---- fast path: if no singular value is thresholded and the truncation loop does not fire, the reference's
+        // d = -G^+ g (source/LOD.cc:667-671) solves the SPD system G d = -g.  Blocked Cholesky (8 x 8 blocks, DMMA
+        // panel and trailing updates on shared-memory tiles), then blocked triangular solves.  Any doubt (tiny pivot,
+        // ||d||_inf close to or above 0.5) goes to the eigen pipeline. ----
+        const int nbk = (n + 7) >> 3;
+        double dmax = 0.0;
+        for (int i = lane; i < n; i += 32) dmax = fmax(dmax, Gf[(i + (i >= d)) * ncd + (i + (i >= d))]);
+        dmax = warp_max(dmax);  // every warp computes it (same value)
+        for (int idx = tid; idx < nbk * (nbk + 1) / 2 * 64; idx += NT) {
+          const int tile = idx >> 6, e = idx & 63, r = e >> 3, c = e & 7;
+          int I = 0;
+          while ((I + 1) * (I + 2) / 2 <= tile) ++I;
+          const int J = tile - I * (I + 1) / 2;
+          const int i = 8 * I + r, j = 8 * J + c;
+          double v;
+          if (i < n && j < n) v = Gf[(i + (i >= d)) * ncd + (j + (j >= d))];
+          else v = (i == j) ? dmax : 0.0;   // padding: pivots equal to the largest diagonal entry
+          sL[tile * 64 + tile_el(r, c)] = v;
         }
-        for (int i = tid; i < n; i += NT) { sg[i] = Gf[(i + (i >= d)) * ncd + d]; sd[i] = -sg[i]; }
-        if (tid == 0) sFlag = 0;
+        for (int i = tid; i < 8 * nbk; i += NT) sz[i] = (i < n) ? -Gf[(i + (i >= d)) * ncd + d] : 0.0;
+        if (tid == 0) { sFlag = 0; sStat[0] = 1e300; sStat[1] = 0.0; }
         __syncthreads();
-        double dmax = 0.0, pmin = 1e300;
-        for (int i = 0; i < n; ++i) dmax = fmax(dmax, Lc[i * (i + 1) / 2 + i]);
-        for (int k = 0; k < n; ++k) {
-          __syncthreads();
-          const double akk = Lc[k * (k + 1) / 2 + k];
-          pmin = fmin(pmin, akk);
-          const double inv = rsqrt(akk);
-          for (int i = k + 1 + tid; i < n; i += NT) {
-            const double v = Lc[i * (i + 1) / 2 + k] * inv;
-            Lc[i * (i + 1) / 2 + k] = v;
-            scol[i] = v;
+        double pmin = 1e300;
+        int bad = 0;
+        for (int K = 0; K < nbk; ++K) {
+          double *dK = sL + tile_off(K, K);
+          if (warp == 0) {  // L_KK^{-1} replaces the diagonal tile (plain row-major)
+            const double2 pv = make_double2(dK[tile_el(g, 2 * t)], dK[tile_el(g, 2 * t + 1)]);
+            double pm;
+            __syncwarp();
+            bad |= chol8_inv(pv.x, pv.y, lane, dK, &pm);
+            pmin = fmin(pmin, pm);
           }
-          if (tid == 0) slam[k] = akk * inv;
           __syncthreads();
-          const int m = n - k - 1;
-          // row i = k+1+warp.., columns by lane: no integer divisions, consecutive addresses
-          for (int ii = warp; ii < m; ii += NWARP) {
-            const int i = k + 1 + ii;
-            const double lik = scol[i];
-            double *row = Lc + i * (i + 1) / 2;
-            for (int j = k + 1 + lane; j <= i; j += 32) row[j] -= lik * scol[j];
+          // panel: L_IK = A_IK L_KK^{-T}
+          for (int I = K + 1 + warp; I < nbk; I += NWARP) {
+            double *tp = sL + tile_off(I, K);
+            const double a0 = tp[tile_el(g, t)], a1 = tp[tile_el(g, 4 + t)];
+            double p0 = 0.0, p1 = 0.0;
+            dmma884(p0, p1, a0, dK[g * 8 + t]);        // B[k][n] = Linv[n][k]
+            dmma884(p0, p1, a1, dK[g * 8 + 4 + t]);
+            __syncwarp();
+            tp[tile_el(g, 2 * t)] = p0;
+            tp[tile_el(g, 2 * t + 1)] = p1;
+          }
+          __syncthreads();
+          // trailing update: A_IJ -= L_IK L_JK^T for K < J <= I
+          const int mrem = nbk - K - 1, ntile = mrem * (mrem + 1) / 2;
+          for (int tt = warp; tt < ntile; tt += 2 * NWARP) {
+            double c0[2], c1[2], a0[2], a1[2], b0[2], b1[2];
+            double *ct[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              int tu = tt + u * NWARP;
+              if (tu >= ntile) tu = tt;
+              int oi = 0;
+              while ((oi + 1) * (oi + 2) / 2 <= tu) ++oi;
+              const int oj = tu - oi * (oi + 1) / 2;
+              const int I = K + 1 + oi, J = K + 1 + oj;
+              ct[u] = sL + tile_off(I, J);
+              const double *ti = sL + tile_off(I, K), *tj = sL + tile_off(J, K);
+              c0[u] = ct[u][tile_el(g, 2 * t)];
+              c1[u] = ct[u][tile_el(g, 2 * t + 1)];
+              a0[u] = -ti[tile_el(g, t)];
+              a1[u] = -ti[tile_el(g, 4 + t)];
+              b0[u] = tj[tile_el(g, t)];       // B[k][n] = L_JK[n][k]
+              b1[u] = tj[tile_el(g, 4 + t)];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) dmma884(c0[u], c1[u], a0[u], b0[u]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) dmma884(c0[u], c1[u], a1[u], b1[u]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (tt + u * NWARP < ntile) {
+                ct[u][tile_el(g, 2 * t)] = c0[u];
+                ct[u][tile_el(g, 2 * t + 1)] = c1[u];
+              }
+          }
+          __syncthreads();
+        }
+        if (warp == 0 && lane == 0) { sStat[0] = pmin; sStat[1] = bad; }
+        // ---- L z = -g (forward), L^T x = z (backward), block by block ----
+        for (int K = 0; K < nbk; ++K) {
+          const double *dK = sL + tile_off(K, K);
+          __syncthreads();
+          double zr = 0.0;
+          if (tid < 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) zr += dK[tid * 8 + c] * sz[8 * K + c];
+          }
+          __syncthreads();
+          if (tid < 8) sz[8 * K + tid] = zr;
+          __syncthreads();
+          for (int idx = tid; idx < (nbk - K - 1) * 8; idx += NT) {
+            const int I = K + 1 + (idx >> 3), r = idx & 7;
+            const double *tp = sL + tile_off(I, K);
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc += tp[tile_el(r, c)] * sz[8 * K + c];
+            sz[8 * I + r] -= acc;
+          }
+        }
+        for (int K = nbk - 1; K >= 0; --K) {
+          const double *dK = sL + tile_off(K, K);
+          __syncthreads();
+          double xr = 0.0;
+          if (tid < 8) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) xr += dK[r * 8 + tid] * sz[8 * K + r];   // L_KK^{-T}
+          }
+          __syncthreads();
+          if (tid < 8) sz[8 * K + tid] = xr;
+          __syncthreads();
+          for (int idx = tid; idx < K * 8; idx += NT) {
+            const int J = idx >> 3, c = idx & 7;
+            const double *tp = sL + tile_off(K, J);
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc += tp[tile_el(r, c)] * sz[8 * K + r];
+            sz[8 * J + c] -= acc;
           }
         }
         __syncthreads();
-        const bool spd_ok = (pmin > 1e-12 * dmax);
+        pmin = sStat[0];
+        const bool spd_ok = (sStat[1] == 0.0) && (pmin > 1e-12 * dmax);
         if (spd_ok && warp == 0) {
-          for (int k = 0; k < n; ++k) {
-            const double zk = sd[k] / slam[k];
-            __syncwarp();
-            if (lane == 0) sd[k] = zk;
-            for (int i = k + 1 + lane; i < n; i += 32) sd[i] -= Lc[i * (i + 1) / 2 + k] * zk;
-            __syncwarp();
-          }
-          for (int k = n - 1; k >= 0; --k) {
-            const double xk = sd[k] / slam[k];
-            __syncwarp();
-            if (lane == 0) sd[k] = xk;
-            const double *row = Lc + k * (k + 1) / 2;
-            for (int j = lane; j < k; j += 32) sd[j] -= row[j] * xk;
-            __syncwarp();
-          }
           double m = 0.0;
-          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sd[r]));
+          for (int r = lane; r < n; r += 32) m = fmax(m, fabs(sz[r]));
           m = warp_max(m);
           if (lane == 0 && m < 0.49) {
             sFlag = 1;
@@ -124,7 +208,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
         if (sFlag) {
           for (int i = warp; i < ncd; i += NWARP) {
             double acc = 0.0;
-            for (int k = lane; k < n; k += 32) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
+            for (int k = lane; k < n; k += 32) acc += sz[k] * Minv[i * ncd + (k + (k >= d))];
             acc = warp_sum(acc);
             if (lane == 0) cv[i] = Minv[i * ncd + d] + acc;
           }

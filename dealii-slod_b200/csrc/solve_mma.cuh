@@ -40,10 +40,10 @@ __device__ __forceinline__ double c_to_b(double c0, double c1, int lane, int j) 
 // operations of the (LDL^T) elimination are applied to an identity tile M alongside, so that after 8 steps
 // M = Ltilde^{-1} and L^{-1} = D^{-1/2} M.  Only the lower triangle of the tile is read.  Writes L^{-1} (row-major
 // 8x8) to sLinv; returns nonzero if a pivot was not positive.
-__device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double *sLinv) {
+__device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double *sLinv, double *pivot_min = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   double m0 = (g == 2 * t) ? 1.0 : 0.0, m1 = (g == 2 * t + 1) ? 1.0 : 0.0;
-  double myinv = 0.0;
+  double myinv = 0.0, pmin = 1e300;
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -54,6 +54,7 @@ __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double 
     const double ac1 = __shfl_sync(0xffffffffu, sel, 4 * (2 * t + 1) + (k >> 1));
     const double mk0 = __shfl_sync(0xffffffffu, m0, 4 * k + t), mk1 = __shfl_sync(0xffffffffu, m1, 4 * k + t);
     if (!(dkk > 0.0)) bad = 1;
+    pmin = fmin(pmin, dkk);
     const double rs = rsqrt(dkk);  // off the dependency chain (only the final scaling needs it)
     myinv = (g == k) ? rs : myinv;
     // 1 / dkk on the chain: MUFU seed + one cubic Newton step (error ~ e^3, e ~ 2^-20)
@@ -68,6 +69,7 @@ __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double 
     m1 -= mg * mk1;
   }
   *reinterpret_cast<double2 *>(sLinv + g * 8 + 2 * t) = make_double2(m0 * myinv, m1 * myinv);
+  if (pivot_min) *pivot_min = pmin;
   __syncwarp();
   return bad;
 }
