@@ -680,6 +680,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     if (getenv("SLOD_FORCE_SIMT_DENSE")) ntile = 0;
     // the register/mma dense stage reads X rows with 16-byte loads: needs the padded layout of the mma solver
     if (ntile && (ctx->mma_variant < 0 || 8 * ntile != sl.ldx)) ntile = 0;
+    if (ipow(P.n + 1, P.dim) > 27) ntile = 0;   // the gather table of M holds 27 local nodes per coarse cell
     if (ntile) {
       const size_t sm = dense_mma_smem(ntile, coef_doubles, nb_max);
       if (sm <= prop.sharedMemPerBlockOptin) {

@@ -31,7 +31,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   double *sT = sM + NC * LDM;             // [kDTB][LDM] W tile, then BD tile
   double *sPivRow = sT + kDTB * LDM;      // [2][NC]
   double *sPivCol = sPivRow + 2 * NC;     // [2][NC]
-  int *sMList = (int *)(sPivCol + 2 * NC);  // [NC][28] X rows of each coarse row: (xrow << 2 | log2 weight), count first
+  int *sMList = (int *)(sPivCol + 2 * NC);  // [NC][32] X rows under each coarse row: (xrow << 2 | log2 weight) or -1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ty = tid >> 4, tx = tid & 15;
@@ -45,28 +45,30 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
     PH_DECL
     load_coef(geo, d_coef, sCoef);
-    // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row ----
-    {
-      const int npc = cP.n + 1;
-      const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;
-      for (int row = tid; row < NC; row += NT) {
-        int cnt = 0;
-        if (row < ncd) {
-          const int comp = row % s;
-          int k[3];
-          col_to_cell(cP, geo, row / s, k);
-          for (int l = 0; l < nloc; ++l) {
-            int tt[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
-            int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
-            if (node_class(cP, geo, a) != 0) continue;
-            int lg = 0;
-            _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim)
-              if (tt[x] != 0 && tt[x] != cP.n) ++lg;
-            if (cnt < 27) sMList[row * 28 + 1 + cnt++] = ((interior_index(geo, a) * s + comp) << 2) | lg;
-          }
+    // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row; one (row, local node) pair per thread,
+    // compacted per row by ballot. ----
+    const int npc = cP.n + 1;
+    const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;   // <= 27 (host guarantees)
+    for (int idx = tid; idx < NC * 32; idx += NT) {
+      const int row = idx >> 5, l = idx & 31;
+      int e = -1;
+      if (row < ncd && l < nloc) {
+        const int comp = row % s;
+        int k[3];
+        col_to_cell(cP, geo, row / s, k);
+        int tt[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
+        int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
+        if (node_class(cP, geo, a) == 0) {
+          int lg = 0;
+          _Pragma("unroll") for (int x = 0; x < 3; ++x) if (x < cP.dim)
+            if (tt[x] != 0 && tt[x] != cP.n) ++lg;
+          e = ((interior_index(geo, a) * s + comp) << 2) | lg;
         }
-        sMList[row * 28] = cnt;
       }
+      // a warp = one row: compact the valid entries to the front (slot order kept), count in slot 31
+      const unsigned mask = __ballot_sync(0xffffffffu, e >= 0);
+      if (e >= 0) sMList[(row << 5) + __popc(mask & ((1u << l) - 1u))] = e;
+      if (l == 31) sMList[idx] = __popc(mask);
     }
     __syncthreads();
 
@@ -80,9 +82,9 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
 #pragma unroll
         for (int j = 0; j < TW; ++j) m[i][j] = 0.0;
         const int row = r0 + i;
-        const int cnt = sMList[row * 28];
+        const int cnt = sMList[row * 32 + 31];
         for (int l = 0; l < cnt; ++l) {
-          const int e = sMList[row * 28 + 1 + l];
+          const int e = sMList[row * 32 + l];
           const double wgt = (double)(1 << (e & 3));
           const double *xr = X + (size_t)(e >> 2) * lay.ldx + tx;
 #pragma unroll

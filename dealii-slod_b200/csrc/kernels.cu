@@ -879,7 +879,7 @@ size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
   (void)nb_max;
   const int NC = 8 * ntile, LDM = NC + 4;
   return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 4 * NC) +
-         sizeof(int) * ((size_t)NC * 28 + 8);
+         sizeof(int) * ((size_t)NC * 32 + 8);
 }
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, const double *W, double *Minv, double *G,
