@@ -57,8 +57,6 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
     }
     __syncthreads();
     const int nbd = sNb;
-    const int nst = (cP.dim == 3) ? 27 : 9;
-    const int per_row = nst * s;
     const int lgn = __ffs(cP.n) - 1;
     for (int t0 = 0; t0 < nbd; t0 += kFTB) {
       const int nt = min(kFTB, nbd - t0);

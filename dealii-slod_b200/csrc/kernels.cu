@@ -312,7 +312,6 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
   int *sAnbr = (int *)(sArow + kTB * 27 * 2);            // [kTB][27*s] interior dof of the neighbour or -1
   int *sBlist = sAnbr + kTB * 27 * 2;                    // [NbMax] boundary dofs
   __shared__ int sNb;
-  __shared__ double sPiv[2];
   const int tid = threadIdx.x, NT = blockDim.x;
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -322,7 +321,7 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
     const double *X = Xbuf + (size_t)w * lay.x_stride;
     __syncthreads();
     load_coef(g, d_coef, sCoef);
-    if (tid == 0) { sNb = 0; sPiv[0] = 0.0; sPiv[1] = 1e300; }
+    if (tid == 0) sNb = 0;
     __syncthreads();
 
     // ---- M = P_i^T X / H^d  (source/LOD.cc:548-551); P is the cell-wise weight stencil ----
