@@ -405,45 +405,40 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       }
       __pipeline_commit();
     };
-    // prologue: stages and Y tiles of the first kSolveStages - 1 steps
-#pragma unroll
-    for (int j = 0; j < kSolveStages - 1; ++j) {
-      if (NBLK - 1 - j >= 0) stage_step(NBLK - 1 - j, (NBLK - 1 - j) & (kSolveStages - 1));
+    // Two block rows per iteration (k and k - 1): both use the same X fragments for all but one term, so a
+    // single pass over the register window feeds four accumulator chains, and the staging / barrier / shift overhead
+    // is paid once per pair.  Stages: buffers (k & 3) and ((k - 1) & 3) are live while the next pair is in flight.
+    static_assert(kSolveStages == 4, "the pairwise backward sweep uses two live and two in-flight stages");
+    auto y_tile = [&](int k) -> double2 {
+      return (k >= 0) ? *reinterpret_cast<const double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t)
+                      : make_double2(0.0, 0.0);
+    };
+    for (int j = 0; j < 2; ++j) {
+      if (NBLK - 1 - j >= 0) stage_step(NBLK - 1 - j, (NBLK - 1 - j) & 3);
       else __pipeline_commit();
     }
-    double2 yq[kSolveStages - 1];
-#pragma unroll
-    for (int j = 0; j < kSolveStages - 1; ++j) {
-      yq[j] = make_double2(0.0, 0.0);
-      if (NBLK - 1 - j >= 0)
-        yq[j] = *reinterpret_cast<const double2 *>(X + (size_t)(8 * (NBLK - 1 - j) + g) * lay.ldx + 8 * warp + 2 * t);
-    }
-    __pipeline_wait_prior(kSolveStages - 2);
+    double2 ya = y_tile(NBLK - 1), yb = y_tile(NBLK - 2);
+    __pipeline_wait_prior(0);
     __syncthreads();
-    for (int k = NBLK - 1; k >= 0; --k) {
+    for (int k = NBLK - 1; k >= 0; k -= 2) {
       PH(6)
-      const int buf = k & (kSolveStages - 1);
-      int nl = NBLK - 1 - k;
+      const bool two = (k >= 1);
+      int nl = NBLK - 1 - k;   // live panel blocks of block row k; block row k - 1 has one more (capped)
       if (nl > RB - 1) nl = RB - 1;
-      const double2 yv = yq[0];
-#pragma unroll
-      for (int j = 0; j < kSolveStages - 2; ++j) yq[j] = yq[j + 1];
-      yq[kSolveStages - 2] = make_double2(0.0, 0.0);
-      if (k - (kSolveStages - 1) >= 0) {
-        const int kn = k - (kSolveStages - 1);
-        stage_step(kn, kn & (kSolveStages - 1));
-        yq[kSolveStages - 2] =
-            *reinterpret_cast<const double2 *>(X + (size_t)(8 * kn + g) * lay.ldx + 8 * warp + 2 * t);
-      } else {
-        __pipeline_commit();
-      }
-      const double *Lp = sLpR + buf * R * 8;
-      const double *Linv = sLinv + buf * 64;
-      // two accumulator chains (odd / even offsets)
-      double c0 = yv.x, c1 = yv.y, e0 = 0.0, e1 = 0.0;
+      int nl2 = NBLK - k;
+      if (nl2 > RB - 1) nl2 = RB - 1;
+      // next pair: stages and Y tiles
+      if (k - 2 >= 0) stage_step(k - 2, (k - 2) & 3); else __pipeline_commit();
+      if (k - 3 >= 0) stage_step(k - 3, (k - 3) & 3); else __pipeline_commit();
+      const double2 yna = y_tile(k - 2), ynb = y_tile(k - 3);
+      const double *Lp = sLpR + (k & 3) * R * 8, *Linv = sLinv + (k & 3) * 64;
+      const double *Lp2 = sLpR + ((k - 1) & 3) * R * 8, *Linv2 = sLinv + ((k - 1) & 3) * 64;
+      double c0 = ya.x, c1 = ya.y, e0 = 0.0, e1 = 0.0;     // block row k     (two chains)
+      double p0 = yb.x, p1 = yb.y, q0 = 0.0, q1 = 0.0;     // block row k - 1 (two chains)
       PH(7)
 #pragma unroll
       for (int off = 1; off < RBMAX; ++off) {
+        // xr[off] = X_{k + off}: offset off for row k, offset off + 1 for row k - 1
         if (off <= nl) {
           // A = Lp^T : A[m = g][kk = 4j + t] = Lp[8 (off-1) + 4j + t][g]
           const double a0 = -Lp[(8 * (off - 1) + t) * 8 + g], a1 = -Lp[(8 * (off - 1) + 4 + t) * 8 + g];
@@ -455,23 +450,52 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
             dmma884(e0, e1, a1, xr[off][1]);
           }
         }
+        if (two && off + 1 <= nl2) {
+          const double a0 = -Lp2[(8 * off + t) * 8 + g], a1 = -Lp2[(8 * off + 4 + t) * 8 + g];
+          if (off & 1) {
+            dmma884(p0, p1, a0, xr[off][0]);
+            dmma884(p0, p1, a1, xr[off][1]);
+          } else {
+            dmma884(q0, q1, a0, xr[off][0]);
+            dmma884(q0, q1, a1, xr[off][1]);
+          }
+        }
       }
       c0 += e0;
       c1 += e1;
       PH(8)
-      // X_D = Linv^T T
+      // X_k = Linv_k^T T
       const double tb0 = c_to_b(c0, c1, lane, 0), tb1 = c_to_b(c0, c1, lane, 1);
       double x0 = 0.0, x1 = 0.0;
       dmma884(x0, x1, Linv[t * 8 + g], tb0);
       dmma884(x0, x1, Linv[(4 + t) * 8 + g], tb1);
       *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(x0, x1);
       const double nb0 = c_to_b(x0, x1, lane, 0), nb1 = c_to_b(x0, x1, lane, 1);
+      double mb0 = 0.0, mb1 = 0.0;
+      if (two) {
+        // the one term of row k - 1 that needs X_k (offset 1), then X_{k-1} = Linv_{k-1}^T T
+        p0 += q0;
+        p1 += q1;
+        dmma884(p0, p1, -Lp2[t * 8 + g], nb0);
+        dmma884(p0, p1, -Lp2[(4 + t) * 8 + g], nb1);
+        const double ub0 = c_to_b(p0, p1, lane, 0), ub1 = c_to_b(p0, p1, lane, 1);
+        double z0 = 0.0, z1 = 0.0;
+        dmma884(z0, z1, Linv2[t * 8 + g], ub0);
+        dmma884(z0, z1, Linv2[(4 + t) * 8 + g], ub1);
+        *reinterpret_cast<double2 *>(X + (size_t)(8 * (k - 1) + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(z0, z1);
+        mb0 = c_to_b(z0, z1, lane, 0);
+        mb1 = c_to_b(z0, z1, lane, 1);
+      }
+      // the register window moves down by two block rows
 #pragma unroll
-      for (int off = RBMAX - 1; off >= 2; --off) { xr[off][0] = xr[off - 1][0]; xr[off][1] = xr[off - 1][1]; }
-      xr[1][0] = nb0;
-      xr[1][1] = nb1;
+      for (int off = RBMAX - 1; off >= 3; --off) { xr[off][0] = xr[off - 2][0]; xr[off][1] = xr[off - 2][1]; }
+      if (RBMAX > 2) { xr[2][0] = nb0; xr[2][1] = nb1; }
+      xr[1][0] = mb0;
+      xr[1][1] = mb1;
+      ya = yna;
+      yb = ynb;
       PH(9)
-      __pipeline_wait_prior(kSolveStages - 2);
+      __pipeline_wait_prior(0);
       __syncthreads();
       PH(10)
     }
