@@ -910,7 +910,7 @@ size_t select_jacobi_smem(int ncd_max) {
   return sizeof(double) * ((size_t)ncd_max * (ncd_max + 1) / 2 + (size_t)ncd_max * ncd_max + 6 * (size_t)ncd_max) +
          sizeof(int) * (3 * (size_t)ncd_max + 8);
 }
-size_t eig_tridiag_smem(int nmax) { return sizeof(double) * ((size_t)nmax * (nmax | 1) + 11 * (size_t)nmax); }
+size_t eig_tridiag_smem(int nmax) { return sizeof(double) * ((size_t)nmax * (nmax | 1) + 4 * (size_t)nmax); }
 size_t eig_ql_smem(int nmax) { return sizeof(double) * 8 * 3 * (size_t)nmax; }
 size_t eig_finish_smem(int nmax) {
   return sizeof(double) * ((size_t)nmax * kEigLd + 5 * (size_t)nmax) + sizeof(int) * ((size_t)nmax + 8);
@@ -934,7 +934,7 @@ cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const 
     SLOD_ATTR(k_eig_finish, pl.smem_fin);
     const long long items_max = (long long)n_work * pl.s;
     for (long long off = 0; off < items_max; off += pl.eig.cap_items) {
-      k_eig_tridiag<<<pl.grid_tri, 256, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
+      k_eig_tridiag<<<pl.grid_tri, 512, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
       k_eig_ql<<<pl.grid_ql, 256, pl.smem_ql, st>>>(ids, b.counters, b.eig_list, (int)off, b.V, b.rot_cs, b.rot_i,
                                                    b.rot_n, pl.eig);
       k_eig_finish<<<pl.grid_fin, 128, pl.smem_fin, st>>>(ids, b.counters, b.eig_list, (int)off, Minv, b.H, b.V,

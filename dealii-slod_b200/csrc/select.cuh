@@ -226,18 +226,20 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
 // Per item in HBM:  Hbuf [n][ldh]  row k = Householder vector v_k (v_k[0] = 1, length n-k-1)
 //                   Vbuf [6][nmax] d | e | tau | g_h | (lambda) | (ghat)
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counters, const int *__restrict__ eig_list,
               int round_off, const double *__restrict__ G_in, double *__restrict__ Hbuf, double *__restrict__ Vbuf,
               EigLayout lay) {
+  // Two barriers per Householder step: every warp recomputes the (cheap) reflector and the vector w redundantly
+  // and keeps v, w lane-distributed in registers (entry i in lane i % 32, slot i / 32), so the only data that has to
+  // cross warps is p = tau A v (after the row-parallel symv) and the updated matrix itself.
   extern __shared__ double smem[];
   const int nmax = lay.nmax, ld = nmax | 1;
   double *sA = smem;                     // [nmax][ld] trailing matrix, both triangles kept up to date
-  double *sv = sA + (size_t)nmax * ld;   // v
+  double *sv = sA + (size_t)nmax * ld;   // v  (identical copies written by every warp)
   double *sw = sv + nmax;                // w
-  double *sgv = sw + nmax;               // g, becomes Q^T g
-  double *sP = sgv + nmax;               // [8][nmax] partial symv sums
-  __shared__ double sTau;
+  double *sgv = sw + nmax;               // g, becomes Q^T g (warp 0)
+  double *sPv = sgv + nmax;              // p = tau A v
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NWARP = NT >> 5;
   int n_items = counters[1] - round_off;
   if (n_items > lay.cap_items) n_items = lay.cap_items;
@@ -257,93 +259,91 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
     __syncthreads();
     for (int k = 0; k < n - 1; ++k) {
       const int m = n - k - 1;  // x = A[k+1 .. n-1][k]
-      if (warp == 0) {
-        // reflector H = I - tau v v^T with H x = beta e_1
-        double xs[8];
-        double sig = 0.0;
+      // ---- reflector H = I - tau v v^T with H x = beta e_1 (every warp) ----
+      double vq[8];
+      double sig = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = lane + 32 * q;
-          xs[q] = (i < m) ? sA[(k + 1 + i) * ld + k] : 0.0;
-          if (i >= 1) sig += xs[q] * xs[q];
-        }
-        sig = warp_sum(sig);
-        const double alpha = __shfl_sync(0xffffffffu, xs[0], 0);
-        double tau = 0.0, beta = alpha, scal = 0.0;
-        if (sig > 0.0) {
-          beta = -copysign(sqrt(alpha * alpha + sig), alpha);
-          tau = (beta - alpha) / beta;
-          scal = 1.0 / (alpha - beta);
-        }
+      for (int q = 0; q < 8; ++q) {
+        const int i = lane + 32 * q;
+        vq[q] = (i < m) ? sA[(k + 1 + i) * ld + k] : 0.0;
+        if (i >= 1) sig += vq[q] * vq[q];
+      }
+      sig = warp_sum(sig);
+      const double alpha = __shfl_sync(0xffffffffu, vq[0], 0);
+      double tau = 0.0, beta = alpha, scal = 0.0;
+      if (sig > 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + sig), alpha);
+        tau = (beta - alpha) / beta;
+        scal = 1.0 / (alpha - beta);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = lane + 32 * q;
+        vq[q] = (i < m) ? ((i == 0) ? 1.0 : vq[q] * scal) : 0.0;
+        if (i < m) sv[i] = vq[q];
+      }
+      if (warp == 0) {
         double gd = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = lane + 32 * q;
           if (i < m) {
-            const double vi = (i == 0) ? 1.0 : xs[q] * scal;
-            xs[q] = vi;
-            sv[i] = vi;
-            H[(size_t)k * lay.ldh + i] = vi;
-            gd += vi * sgv[k + 1 + i];
+            H[(size_t)k * lay.ldh + i] = vq[q];
+            gd += vq[q] * sgv[k + 1 + i];
           }
         }
         gd = warp_sum(gd) * tau;  // g <- H g
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = lane + 32 * q;
-          if (i < m) sgv[k + 1 + i] -= gd * xs[q];
+          if (i < m) sgv[k + 1 + i] -= gd * vq[q];
         }
         if (lane == 0) {
-          sTau = tau;
           V[k] = sA[k * ld + k];       // d_k
           V[nmax + k] = beta;          // e_k
           V[2 * nmax + k] = tau;
         }
       }
-      __syncthreads();
-      const double tau = sTau;
-      if (tau != 0.0) {
-        // p = A22 v : thread (part, i) sums columns j = part, part + parts, ... of row i (read as column i: conflict free)
-        const int mp = (m + 31) & ~31;
-        int parts = NT / mp;
-        if (parts > 8) parts = 8;
-        {
-          const int part = tid / mp, i = tid - part * mp;
-          if (part < parts && i < m) {
-            double acc = 0.0;
-            for (int j = part; j < m; j += parts) acc += sA[(k + 1 + j) * ld + (k + 1 + i)] * sv[j];
-            sP[part * nmax + i] = acc;
-          }
-        }
-        __syncthreads();
-        if (warp == 0) {
-          double ps[8];
-          double dot = 0.0;
+      if (tau != 0.0) {   // identical in every warp (same data, same arithmetic)
+        // ---- p = tau A22 v : one row per warp pass, lanes over the columns ----
+        for (int i = warp; i < m; i += NWARP) {
+          const double *row = sA + (k + 1 + i) * ld + (k + 1);
+          double acc = 0.0;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const int i = lane + 32 * q;
-            double acc = 0.0;
-            if (i < m) {
-              for (int pp = 0; pp < parts; ++pp) acc += sP[pp * nmax + i];
-              acc *= tau;
-              dot += acc * sv[i];
-            }
-            ps[q] = acc;
+            const int j = lane + 32 * q;
+            if (j < m) acc += row[j] * vq[q];
           }
-          dot = warp_sum(dot);
-          const double al = -0.5 * tau * dot;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i = lane + 32 * q;
-            if (i < m) sw[i] = ps[q] + al * sv[i];
-          }
+          acc = warp_sum(acc);
+          if (lane == 0) sPv[i] = tau * acc;
         }
         __syncthreads();
-        // A22 <- A22 - v w^T - w v^T
+        // ---- w = p - (tau/2)(p.v) v  (every warp), A22 <- A22 - v w^T - w v^T ----
+        double wq[8];
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = lane + 32 * q;
+          wq[q] = (i < m) ? sPv[i] : 0.0;
+          dot += wq[q] * vq[q];
+        }
+        dot = warp_sum(dot);
+        const double al = -0.5 * tau * dot;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = lane + 32 * q;
+          wq[q] += al * vq[q];
+          if (i < m) sw[i] = wq[q];
+        }
+        __syncwarp();
         for (int i = warp; i < m; i += NWARP) {
           const double vi = sv[i], wi = sw[i];
           double *row = sA + (k + 1 + i) * ld + (k + 1);
-          for (int j = lane; j < m; j += 32) row[j] -= vi * sw[j] + wi * sv[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int j = lane + 32 * q;
+            if (j < m) row[j] -= vi * wq[q] + wi * vq[q];
+          }
         }
       }
       __syncthreads();
