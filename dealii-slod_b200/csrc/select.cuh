@@ -532,11 +532,15 @@ k_eig_finish(const int *__restrict__ patch_ids, int *__restrict__ counters, cons
       if (warp == 0) {
         int cur = -1;
         double carry = 0.0;
+        // chunks of 32 rotations, one per lane, the next chunk is in flight while the current one is replayed
+        double2 rcn = make_double2(1.0, 0.0);
+        int idxn = 0;
+        if (nrot - 1 - lane >= 0) { rcn = cs[nrot - 1 - lane]; idxn = ri[nrot - 1 - lane]; }
         for (int q0 = nrot; q0 > 0; q0 -= 32) {
-          const int q = q0 - 1 - lane;
-          double2 rc = make_double2(1.0, 0.0);
-          int idx = 0;
-          if (q >= 0) { rc = cs[q]; idx = ri[q]; }
+          const double2 rc = rcn;
+          const int idx = idxn;
+          const int qn = q0 - 33 - lane;
+          if (qn >= 0) { rcn = cs[qn]; idxn = ri[qn]; }
           const int cnt = min(32, q0);
           for (int j = 0; j < cnt; ++j) {
             const double c = __shfl_sync(0xffffffffu, rc.x, j), sn = __shfl_sync(0xffffffffu, rc.y, j);
