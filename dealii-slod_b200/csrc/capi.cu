@@ -718,7 +718,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   FinishLayout &fl = ctx->fl;
   fl.ell_width = P.ell_width;
   fl.coef_doubles = coef_doubles; fl.nf_max = P.NfMax; fl.ncd_max = P.NcdMax; fl.ldx = sl.ldx; fl.x_stride = sl.x_stride;
-  ctx->smem_finish = sizeof(double) * ((size_t)coef_doubles + P.NfMax + P.NcdMax);
+  ctx->smem_finish = sizeof(double) * ((size_t)coef_doubles + P.NfMax + P.NcdMax) + sizeof(int) * ((size_t)P.NiMax + 2);
   ctx->smem_coarse = sizeof(double) * ((size_t)P.s * P.NfMax);
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
   {

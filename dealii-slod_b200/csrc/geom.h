@@ -58,10 +58,9 @@ SLOD_HD uint32_t morton_encode(const int idx[3], int dim, int ref) {
   return code;
 }
 
-SLOD_HD Geom make_geom(const Params &P, int pid) {
+// patch geometry from the coordinates of its centre cell
+SLOD_HD Geom make_geom_at(const Params &P, const int c[3]) {
   Geom g;
-  int c[3];
-  morton_decode((uint32_t)pid, P.dim, P.ref, c);
   g.full = 1;
   g.Nc = 1;
   g.nnodes = 1;
@@ -104,6 +103,11 @@ SLOD_HD Geom make_geom(const Params &P, int pid) {
   if (P.quirk_presaved && g.full && P.has_presaved)
     for (int a = 0; a < 3; ++a) g.clo[a] = P.presaved_lo[a];
   return g;
+}
+SLOD_HD Geom make_geom(const Params &P, int pid) {
+  int c[3];
+  morton_decode((uint32_t)pid, P.dim, P.ref, c);
+  return make_geom_at(P, c);
 }
 
 // list position (coarse column / spacedim) of patch cell k (relative coordinates)

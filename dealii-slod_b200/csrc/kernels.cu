@@ -489,6 +489,7 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
   double *sCoef = smem;
   double *sPhi = sCoef + lay.coef_doubles;  // [Nf]
   double *sC = sPhi + lay.nf_max;           // [ncd]
+  int *sRowDof = (int *)(sC + lay.ncd_max);  // [Ni] patch dof of every interior row
   __shared__ double sRed[32];
   __shared__ double sNorm;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
@@ -500,6 +501,11 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
     const double *X = Xbuf + (size_t)w * lay.x_stride;
     __syncthreads();
     load_coef(g, d_coef, sCoef);
+    for (int r = tid; r < g.Ni; r += NT) {
+      int a[3], ca;
+      idof_to_node(g, r, a, ca);
+      sRowDof[r] = node_index(g, a) * s + ca;
+    }
     for (int d = 0; d < s; ++d) {
       __syncthreads();
       for (int i = tid; i < ncd; i += NT) sC[i] = cvec[((size_t)w * s + d) * lay.ncd_max + i];
@@ -521,9 +527,7 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (r0 + u < g.Ni) {
-              int a[3], ca;
-              idof_to_node(g, r0 + u, a, ca);
-              sPhi[node_index(g, a) * s + ca] = acc[u];
+              sPhi[sRowDof[r0 + u]] = acc[u];
               nrm += acc[u] * acc[u];
             }
           }
@@ -739,7 +743,7 @@ k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi,
       for (int a = 0; a < DIM; ++a) inside = inside && (qc[a] >= 0 && qc[a] < cP.N);
       if (!inside) continue;
       const int qid = (int)morton_encode(qc, DIM, cP.ref);
-      const Geom gq = make_geom(cP, qid);
+      const Geom gq = make_geom_at(cP, qc);
       // sweep box = box(q) /\ common box, in global node coordinates
       int b0[3], b1[3];
       bool any = true;
