@@ -512,23 +512,55 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
       for (int i = tid; i < g.Nf; i += NT) sPhi[i] = 0.0;
       __syncthreads();
       double nrm = 0.0;
-      // four rows of X per warp iteration: 16 independent 256-byte loads in flight per warp
-      for (int r0 = 4 * warp; r0 < g.Ni; r0 += 4 * nwarp) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      if ((lay.ldx & 3) == 0) {
+        // eight rows of X per warp iteration, a lane reads 4 consecutive columns of each with two 16-byte loads
+        // (16 independent loads in flight per lane) and keeps its 4 entries of c in registers
+        double cc[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = min(r0 + u, g.Ni - 1);
-#pragma unroll 4
-          for (int col = lane; col < ncd; col += 32) acc[u] += X[(size_t)r * lay.ldx + col] * sC[col];
+        for (int q = 0; q < 4; ++q) cc[q] = (4 * lane + q < ncd) ? sC[4 * lane + q] : 0.0;
+        const bool in_row = 4 * lane + 3 < lay.ldx;
+        for (int r0 = 8 * warp; r0 < g.Ni; r0 += 8 * nwarp) {
+          double acc[8];
+          double2 xa[8], xb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = min(r0 + u, g.Ni - 1);
+            const double2 *xp = reinterpret_cast<const double2 *>(X + (size_t)r * lay.ldx + 4 * lane);
+            xa[u] = in_row ? xp[0] : make_double2(0.0, 0.0);
+            xb[u] = in_row ? xp[1] : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            acc[u] = warp_sum((xa[u].x * cc[0] + xa[u].y * cc[1]) + (xb[u].x * cc[2] + xb[u].y * cc[3]));
+          if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (r0 + u < g.Ni) {
+                sPhi[sRowDof[r0 + u]] = acc[u];
+                nrm += acc[u] * acc[u];
+              }
+            }
+          }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
-        if (lane == 0) {
+      } else {
+        // generic layout (SIMT solver): four rows per warp iteration, scalar loads
+        for (int r0 = 4 * warp; r0 < g.Ni; r0 += 4 * nwarp) {
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (r0 + u < g.Ni) {
-              sPhi[sRowDof[r0 + u]] = acc[u];
-              nrm += acc[u] * acc[u];
+            const int r = min(r0 + u, g.Ni - 1);
+#pragma unroll 4
+            for (int col = lane; col < ncd; col += 32) acc[u] += X[(size_t)r * lay.ldx + col] * sC[col];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+          if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (r0 + u < g.Ni) {
+                sPhi[sRowDof[r0 + u]] = acc[u];
+                nrm += acc[u] * acc[u];
+              }
             }
           }
         }
