@@ -481,7 +481,7 @@ namespace slod {
 // ------------------------------------------------------------------------------------------------
 // k_patch_finish : phi = X c (zero on every boundary dof), normalise, A phi
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
                const double *__restrict__ Xbuf, const double *__restrict__ cvec, double *__restrict__ phi_out,
                double *__restrict__ aphi_out, FinishLayout lay) {
