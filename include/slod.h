@@ -17,6 +17,9 @@
  *  - one handle drives ONE CUDA device (one process per GPU; the collective between ranks is done
  *    by the caller on the device buffers, see slod_*_device entry points).
  *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
+ *  - a handle is thread-compatible, not thread-safe; the kernels read their parameters from one __constant__ block
+ *    per process, so compute calls of DIFFERENT handles of one process must not overlap in time either (sequential
+ *    use of several handles is fine and tested).
  *  - patch id == active-cell index of the centre cell after refine_global (Morton / Z-order, x low
  *    bit), exactly as in source/LOD.cc:184-192.
  *  - patch-local fine nodes are numbered lexicographically (x fastest) on the patch's own node box
@@ -117,8 +120,8 @@ int slod_free_host(void *p);
 
 /* diagnostics: per patch and component 8 doubles:
  *   [0] ||d||_inf before truncation  [1] truncation steps  [2] sigma_0  [3] smallest kept sigma
- *   [4] cond(M) estimate (max/min Cholesky pivot squared) [5] selection path (0 LOD, 1 Cholesky, 2 eigen)
- *   [6] Jacobi sweeps [7] status bits */
+ *   [4] reserved  [5] selection path (0 LOD branch, 1 Cholesky fast path, 2 Jacobi fallback, 3 tridiagonal QL)
+ *   [6] QL iterations / Jacobi sweeps [7] status bits */
 int slod_get_patch_diagnostics(const slod_ctx *ctx, int64_t patch, int comp, double out[8]);
 /* stage intermediates of one patch for staged parity tests (recomputed on demand for that patch):
  * X = A_ii^{-1} P_i  (n_internal x n_coarse, row-major), Minv (n_coarse^2), BD^T BD (n_coarse^2). Any may be NULL. */
