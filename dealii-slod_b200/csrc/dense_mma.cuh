@@ -35,7 +35,9 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ty = tid >> 4, tx = tid & 15;
-  const int r0 = 4 * ty;
+  // coarse rows of this thread in the M accumulation: ty, ty + NT/16, ... (interleaved: rows near the patch boundary
+  // have fewer interior nodes under them, consecutive rows would leave some warps with much less to gather)
+  constexpr int RSTR = 2 * NTILE;
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int pid = patch_ids[w];
@@ -81,7 +83,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int j = 0; j < TW; ++j) m[i][j] = 0.0;
-        const int row = r0 + i;
+        const int row = ty + RSTR * i;
         const int cnt = sMList[row * 32 + 31];
         for (int l = 0; l < cnt; ++l) {
           const int e = sMList[row * 32 + l];
@@ -107,7 +109,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < TW; ++j) sM[(r0 + i) * LDM + tx + 16 * j] = m[i][j];
+        for (int j = 0; j < TW; ++j) sM[(ty + RSTR * i) * LDM + tx + 16 * j] = m[i][j];
       __syncthreads();
       int badpiv = 0;
       const int nblk = (ncd + 7) >> 3;
