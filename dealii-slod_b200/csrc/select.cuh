@@ -410,19 +410,24 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
             double sn = 1.0, c = 1.0, p = 0.0;
             int i = m - 1;
             // operands of rotation i travel in registers: the next ones are fetched one rotation ahead, and what
-            // rotation i + 1 produced for position i + 1 is handed over instead of going through shared memory
-            double e_i = se[i], d_lo = sd[i], d_hi = sd[i + 1], gh_lo = sgh[i], gh_hi = sgh[i + 1];
-            for (; i >= l; --i) {
+            // rotation i + 1 produced for position i + 1 is handed over instead of going through shared memory.
+            // Running pointers instead of indices: the loop is bound by its instruction count (one warp, dependent
+            // issue), not by any pipe.
+            double *pe = se + i, *pd = sd + i, *pg = sgh + i;
+            double2 *pcs = cs + nrot;
+            unsigned short *pri = ri + nrot;
+            double e_i = pe[0], d_lo = pd[0], d_hi = pd[1], gh_lo = pg[0], gh_hi = pg[1];
+            for (; i >= l; --i, --pe, --pd, --pg) {
               double e_n = 0.0, d_n = 0.0, gh_n = 0.0;
-              if (i > l) { e_n = se[i - 1]; d_n = sd[i - 1]; gh_n = sgh[i - 1]; }
+              if (i > l) { e_n = pe[-1]; d_n = pd[-1]; gh_n = pg[-1]; }
               const double f = sn * e_i;
               const double b = c * e_i;
               const double h2 = f * f + gg * gg;
               const double ir = rsqrt(h2);   // one MUFU-based op on the dependency chain instead of sqrt + divide
               r = (h2 > 0.0) ? h2 * ir : 0.0;
-              se[i + 1] = r;
+              pe[1] = r;
               if (r == 0.0) {
-                sd[i + 1] = d_hi - p;
+                pd[1] = d_hi - p;
                 se[m] = 0.0;
                 break;
               }
@@ -431,15 +436,17 @@ k_eig_ql(const int *__restrict__ patch_ids, const int *__restrict__ counters, co
               gg = d_hi - p;
               r = (d_lo - gg) * sn + 2.0 * c * b;
               p = sn * r;
-              sd[i + 1] = gg + p;
+              pd[1] = gg + p;
               gg = c * r - b;
               // Z <- Z R : columns (i, i+1); here applied as x <- R^T x to g_h
-              sgh[i + 1] = sn * gh_lo + c * gh_hi;
+              pg[1] = sn * gh_lo + c * gh_hi;
               gh_hi = c * gh_lo - sn * gh_hi;
               if (lane == 0) {
-                cs[nrot] = make_double2(c, sn);
-                ri[nrot] = (unsigned short)i;
+                *pcs = make_double2(c, sn);
+                *pri = (unsigned short)i;
               }
+              ++pcs;
+              ++pri;
               ++nrot;
               e_i = e_n; d_hi = d_lo; d_lo = d_n; gh_lo = gh_n;
             }
