@@ -344,6 +344,29 @@ def main():
         e2e = {"value": n / dt, "unit": "patches/s", "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "path": path}
 
+    # Online phase on the handle's own basis and coarse matrix: informational, outside the metric.
+    # f = 1 per component (closed form of the Gauss sums: h^dim at interior nodes, 0 on the boundary).
+    online = None
+    if e2e is not None and world == 1:
+        G = (2 ** w["ref"]) * w["n"] + 1
+        w1 = np.full(G, 1.0 / (G - 1))
+        w1[0] = w1[-1] = 0.0
+        f = w1
+        for _ in range(w["dim"] - 1):
+            f = np.multiply.outer(w1, f)
+        f = np.repeat(f.ravel(), s)
+        t0 = time.perf_counter()
+        b = ctx.coarse_rhs(f)
+        t1 = time.perf_counter()
+        u, cg_steps, cg_res = ctx.coarse_solve(b, max_steps=20000, tolerance=0.0, reduction=1e-10)
+        t2 = time.perf_counter()
+        uh = ctx.prolongate(u)
+        t3 = time.perf_counter()
+        online = {"coarse_rhs_ms": (t1 - t0) * 1e3, "coarse_cg_ms": (t2 - t1) * 1e3, "cg_steps": int(cg_steps),
+                  "cg_reduction": 1e-10, "cg_residual": float(cg_res), "prolongate_ms": (t3 - t2) * 1e3,
+                  "u_fine_l2": float(np.linalg.norm(uh)),
+                  "note": "host-buffer C ABI calls (copies included), forcing f = 1, diag(K)-preconditioned CG"}
+
     if rank == 0:
         fm = flop_model(w)
         names = ["patch_solve", "patch_dense", "patch_select", "patch_finish"]
@@ -379,7 +402,7 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_of(w, args.workload), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "offline_wall_ms": ms_step}
+                "offline_wall_ms": ms_step, "online": online}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

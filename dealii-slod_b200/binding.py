@@ -26,7 +26,7 @@ EXPORTS = [
     "slod_basis_stride", "slod_get_all_basis", "slod_assemble_coarse", "slod_get_coarse_csr",
     "slod_get_patch_diagnostics", "slod_debug_patch_stages", "slod_get_timings", "slod_compute_basis_device",
     "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
-    "slod_free_host",
+    "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
 ]
 
 
@@ -64,6 +64,10 @@ def load_library():
     lib.slod_last_create_error.restype = C.c_char_p
     lib.slod_set_coefficient.argtypes = [vp, C.c_int, C.c_int, P(dbl), C.c_size_t]
     lib.slod_patch_count.argtypes = [vp, P(i64)]
+    lib.slod_fine_size.argtypes = [vp, P(i64)]
+    lib.slod_coarse_rhs.argtypes = [vp, P(dbl), P(dbl)]
+    lib.slod_coarse_solve.argtypes = [vp, P(dbl), P(dbl), i32, dbl, dbl, P(i32), P(dbl)]
+    lib.slod_prolongate.argtypes = [vp, P(dbl), P(dbl)]
     lib.slod_get_patch_info.argtypes = [vp, i64] + [P(i32)] * 6 + [P(i32), P(i32)]
     lib.slod_get_patch_cells.argtypes = [vp, i64, P(C.c_uint32), P(i32)]
     lib.slod_get_patch_fine_dofs.argtypes = [vp, i64, P(C.c_uint64), P(i32)]
@@ -233,6 +237,40 @@ class SlodContext:
         self._ck(self.lib.slod_get_coarse_csr(self.h, rowptr.ctypes.data_as(i64p), col.ctypes.data_as(i64p),
                                               _dp(val), C.byref(nr), C.byref(nnz)))
         return rowptr, col, val
+
+    # -- online phase (LOD::solve, source/LOD.cc:975-1001; prolongation :1251) --
+    @property
+    def n_fine(self):
+        n = C.c_int64()
+        self._ck(self.lib.slod_fine_size(self.h, C.byref(n)))
+        return n.value
+
+    def coarse_rhs(self, f_fine):
+        f = np.ascontiguousarray(f_fine, dtype=np.float64).ravel()
+        if f.size != self.n_fine:
+            raise ValueError(f"fine vector has {f.size} entries, expected {self.n_fine}")
+        b = np.empty(self.n_patches * self.s)
+        self._ck(self.lib.slod_coarse_rhs(self.h, _dp(f), _dp(b)))
+        return b
+
+    def coarse_solve(self, rhs, max_steps=10000, tolerance=1e-10, reduction=1e-10):
+        """Returns (u, steps, residual); raises SlodError (SLOD_ERR_NUMERIC) when CG does not converge."""
+        b = np.ascontiguousarray(rhs, dtype=np.float64).ravel()
+        if b.size != self.n_patches * self.s:
+            raise ValueError("coarse vector has the wrong size")
+        u = np.empty_like(b)
+        steps, res = C.c_int32(), C.c_double()
+        self._ck(self.lib.slod_coarse_solve(self.h, _dp(b), _dp(u), max_steps, tolerance, reduction,
+                                            C.byref(steps), C.byref(res)))
+        return u, steps.value, res.value
+
+    def prolongate(self, u_coarse):
+        u = np.ascontiguousarray(u_coarse, dtype=np.float64).ravel()
+        if u.size != self.n_patches * self.s:
+            raise ValueError("coarse vector has the wrong size")
+        out = np.empty(self.n_fine)
+        self._ck(self.lib.slod_prolongate(self.h, _dp(u), _dp(out)))
+        return out
 
     def diagnostics(self, patch, comp=0):
         out = np.empty(8)

@@ -1082,6 +1082,102 @@ int slod_get_coarse_csr(const slod_ctx *cctx, int64_t *rowptr, int64_t *col, dou
   return SLOD_OK;
 }
 
+// ---- online phase on the handle's own basis and coarse matrix ----
+int slod_fine_size(const slod_ctx *ctx, int64_t *n_fine) {
+  if (!ctx || !n_fine) return SLOD_ERR_INVALID;
+  int64_t n = ctx->P.s;
+  for (int a = 0; a < ctx->P.dim; ++a) n *= (int64_t)ctx->P.nsub + 1;
+  *n_fine = n;
+  return SLOD_OK;
+}
+
+int slod_coarse_rhs(slod_ctx *ctx, const double *f_fine, double *rhs_coarse) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  if (!f_fine || !rhs_coarse) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  CK(upload_params(ctx->P));
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
+  double *d_f = nullptr, *d_b = nullptr;
+  CK(cudaMalloc(&d_f, sizeof(double) * (size_t)n_fine));
+  cudaError_t e = cudaMalloc(&d_b, sizeof(double) * nc);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, f_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = launch_coarse_rhs(0, (int)ctx->n_patches, ctx->P.s, ctx->d_phi, d_f, d_b, ctx->P.NfMax);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rhs_coarse, d_b, sizeof(double) * nc, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_f);
+  cudaFree(d_b);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_coarse_rhs: ") + cudaGetErrorString(e));
+  return SLOD_OK;
+}
+
+int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse, int32_t max_steps, double tolerance,
+                      double reduction, int32_t *steps, double *residual) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->coarse_done) return fail(ctx, SLOD_ERR_STATE, "slod_assemble_coarse has not run");
+  if (!rhs_coarse || !u_coarse) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  if (max_steps < 0 || !(tolerance >= 0.0) || !(reduction >= 0.0))
+    return fail(ctx, SLOD_ERR_INVALID, "solver control: max_steps, tolerance and reduction must be non-negative");
+  CK(cudaSetDevice(ctx->device));
+  CK(upload_params(ctx->P));
+  const int nrows = (int)(ctx->n_patches * ctx->P.s);
+  double *d_b = nullptr, *d_x = nullptr, *d_work = nullptr;
+  CK(cudaMalloc(&d_b, sizeof(double) * 2 * (size_t)nrows));
+  d_x = d_b + nrows;
+  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(nrows));
+  int st_steps = 0, flag = 0;
+  long long n_launch = 0;
+  double res = 0.0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, rhs_coarse, sizeof(double) * nrows, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess)
+    e = run_coarse_cg(0, nrows, ctx->d_Kell, d_b, d_x, d_work, max_steps, tolerance, reduction, &st_steps, &res, &flag,
+                      &n_launch);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_coarse, d_x, sizeof(double) * nrows, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_b);
+  cudaFree(d_work);
+  ctx->launches += n_launch;
+  if (steps) *steps = st_steps;
+  if (residual) *residual = res;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_coarse_solve: ") + cudaGetErrorString(e));
+  if (flag == 2) return fail(ctx, SLOD_ERR_NUMERIC, "coarse CG broke down: the coarse matrix is not positive definite");
+  if (flag != 1) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "coarse CG did not converge: %d steps, residual %.3e", st_steps, res);
+    return fail(ctx, SLOD_ERR_NUMERIC, buf);   // deal.II throws SolverControl::NoConvergence here
+  }
+  return SLOD_OK;
+}
+
+int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  if (!u_coarse || !u_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  CK(upload_params(ctx->P));
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
+  double *d_u = nullptr, *d_f = nullptr;
+  CK(cudaMalloc(&d_u, sizeof(double) * nc));
+  cudaError_t e = cudaMalloc(&d_f, sizeof(double) * (size_t)n_fine);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u_coarse, sizeof(double) * nc, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = launch_prolongate(0, n_fine, ctx->d_phi, d_u, d_f, ctx->P.NfMax);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_fine, d_f, sizeof(double) * (size_t)n_fine, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_u);
+  cudaFree(d_f);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_prolongate: ") + cudaGetErrorString(e));
+  return SLOD_OK;
+}
+
 /* pinned host memory for the caller-owned output buffers (device->host copies into pageable memory run at a
  * fraction of the link speed) */
 int slod_alloc_host(size_t bytes, void **out) {

@@ -1002,6 +1002,62 @@ cudaError_t launch_gather(cudaStream_t st, const double *src, const long long *p
   k_gather<<<148 * 8, 256, 0, st>>>(src, perm, dst, n);
   return cudaGetLastError();
 }
+}  // namespace slod
+#include "online.cuh"
+namespace slod {
+
+cudaError_t launch_coarse_rhs(cudaStream_t st, int n_patches, int s, const double *phi, const double *f, double *b,
+                              int nf_max) {
+  const int rows = n_patches * s, per = kCgThreads / 32;
+  k_coarse_rhs<<<(rows + per - 1) / per, kCgThreads, 0, st>>>(n_patches, phi, f, b, nf_max);
+  return cudaGetLastError();
+}
+cudaError_t launch_prolongate(cudaStream_t st, long long n_fine, const double *phi, const double *u, double *u_fine,
+                              int nf_max) {
+  const long long blocks = (n_fine + kCgThreads - 1) / kCgThreads;
+  k_prolongate<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), kCgThreads, 0, st>>>(n_fine, phi, u, u_fine, nf_max);
+  return cudaGetLastError();
+}
+size_t cg_workspace_doubles(int nrows) {
+  const int nb_spmv = (nrows + kCgThreads / 32 - 1) / (kCgThreads / 32), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+  // r, p, q, dinv | partial p.q | partial r.z, r.r | state
+  return (size_t)4 * nrows + nb_spmv + 2 * (size_t)nb_vec + (sizeof(CgState) + 7) / 8;
+}
+// Runs preconditioned CG until the device-side stopping test fires or max_steps is reached; the host looks at the
+// state every `check_every` steps (one 64-byte copy).  Returns the state in *steps / *residual / *flag.
+cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const double *b, double *x, double *work,
+                          int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
+                          long long *launches) {
+  const int per = kCgThreads / 32;
+  const int nb_spmv = (nrows + per - 1) / per, nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+  double *r = work, *p = r + nrows, *q = p + nrows, *dinv = q + nrows;
+  double *ppq = dinv + nrows, *prz = ppq + nb_spmv, *prr = prz + nb_vec;
+  CgState *state = reinterpret_cast<CgState *>(prr + nb_vec);
+  CgState h{};
+  cudaError_t e;
+  k_cg_init<<<1, 1024, 0, st>>>(nrows, Kell, b, x, r, p, dinv, state, tol, reduction);
+  *launches += 1;
+  const int check_every = 16;
+  int it = 0;
+  for (;;) {
+    if ((e = cudaMemcpyAsync(&h, state, sizeof(CgState), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (h.done || it >= max_steps) break;
+    const int upto = (it + check_every < max_steps) ? it + check_every : max_steps;
+    for (; it < upto; ++it) {
+      k_cg_spmv<<<nb_spmv, kCgThreads, 0, st>>>(nrows, Kell, p, q, ppq, state);
+      k_cg_update<<<nb_vec, kCgThreads, 0, st>>>(nrows, it, p, q, dinv, x, r, ppq, nb_spmv, prz, prr, state);
+      k_cg_direction<<<nb_vec, kCgThreads, 0, st>>>(nrows, it, r, dinv, p, prz, prr, nb_vec, state);
+      *launches += 3;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  *steps = h.steps;
+  *residual = sqrt(h.rr);
+  *flag = h.done;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay) {
   cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -111,6 +111,15 @@ size_t coarse_blocked_smem(int dim, int s, int NU);
 cudaError_t launch_coarse_blocked(int dim, int s, int grid, size_t smem, cudaStream_t st, int p0, int p1,
                                   const double *phi, const double *aphi, double *Kell, const FinishLayout &lay, int NU);
 cudaError_t launch_gather(cudaStream_t st, const double *src, const long long *perm, double *dst, long long n);
+// online phase (online.cuh): b = C^T f, CG on the block-ELL coarse matrix, u_h = C u
+cudaError_t launch_coarse_rhs(cudaStream_t st, int n_patches, int s, const double *phi, const double *f, double *b,
+                              int nf_max);
+cudaError_t launch_prolongate(cudaStream_t st, long long n_fine, const double *phi, const double *u, double *u_fine,
+                              int nf_max);
+size_t cg_workspace_doubles(int nrows);
+cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const double *b, double *x, double *work,
+                          int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
+                          long long *launches);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);
 

@@ -1,0 +1,261 @@
+// Coarse right-hand side, coarse solve and prolongation: what LOD::solve() and the first
+// lines of LOD::compare_lod_with_fem() do with the basis and the coarse matrix the offline phase produced
+// (source/LOD.cc:975-1001, :1251).
+//
+//   k_coarse_rhs   b = C^T f           basis_matrix_transposed.Tvmult(system_rhs, fem_rhs)        source/LOD.cc:981
+//   k_cg_*         K u = b             SolverCG + ReductionControl                                source/LOD.cc:991-998
+//   k_prolongate   u_h = C u           basis_matrix_transposed.vmult(lod_solution, solution)      source/LOD.cc:1251
+//
+// C is never formed: column (patch, d) of C is the patch-local vector phi_{patch,d} placed on the patch's node box, so
+// both products are box-indexed gathers.  K is used in the block-ELL form k_coarse_blocked wrote (slot = neighbour
+// offset, the column index is the Morton code of the neighbour cell).  Fine vectors are lexicographic: node
+// (x fastest) * spacedim + component.  Every reduction has a fixed order (no atomics): results are bit-reproducible.
+// The preconditioner is the diagonal of K instead of the reference's SSOR(1.2) sweep -- a triangular sweep over a
+// matrix with (4 ell + 3)^dim entries per row has no parallelism to speak of, and the stopping rule (residual
+// reduction) is the same, so the solutions agree to the tolerance, not the iteration counts.
+// Included by kernels.cu.
+#pragma once
+
+namespace slod {
+
+constexpr int kCgThreads = 256;
+
+// fixed-order block sum; every thread returns the total.  sRed: blockDim.x / 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *sRed) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sRed[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += sRed[i];
+  return t;
+}
+// sum of a short global array in a fixed order, the same in every block
+__device__ __forceinline__ double array_sum(const double *__restrict__ a, int n, double *sRed) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += a[i];
+  return block_sum(v, sRed);
+}
+
+// one warp per coarse dof (patch, d): dot product of phi with f on the patch's node box
+__global__ void __launch_bounds__(kCgThreads)
+k_coarse_rhs(int n_patches, const double *__restrict__ phi, const double *__restrict__ f, double *__restrict__ b,
+             int nf_max) {
+  const int s = cP.s, n = cP.n;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_patches * s) return;
+  const int pid = row / s;
+  const Geom g = make_geom(cP, pid);
+  const int G = cP.nsub + 1;
+  const double *pp = phi + (size_t)row * nf_max;
+  const int xs = g.p[0] * s;   // contiguous run: one x line of nodes with their components
+  double acc = 0.0;
+  for (int z = 0; z < g.p[2]; ++z)
+    for (int y = 0; y < g.p[1]; ++y) {
+      const double *pl = pp + (size_t)(z * g.p[1] + y) * xs;
+      const double *fl = f + (((size_t)(g.lo[2] * n + z) * G + (g.lo[1] * n + y)) * G + g.lo[0] * n) * s;
+      for (int i = lane; i < xs; i += 32) acc += pl[i] * fl[i];
+    }
+  acc = warp_sum(acc);
+  if (lane == 0) b[row] = acc;
+}
+
+// one thread per fine dof: sum over the patches whose node box contains the node, in ascending centre order
+__global__ void __launch_bounds__(kCgThreads)
+k_prolongate(long long n_fine, const double *__restrict__ phi, const double *__restrict__ u,
+             double *__restrict__ u_fine, int nf_max) {
+  const int s = cP.s, n = cP.n, ell = cP.ell, dim = cP.dim;
+  const int G = cP.nsub + 1;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_fine;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int comp = (int)(idx % s);
+    long long node = idx / s;
+    int a[3];
+    a[0] = (int)(node % G);
+    node /= G;
+    a[1] = (dim >= 2) ? (int)(node % G) : 0;
+    a[2] = (dim == 3) ? (int)(node / G) : 0;
+    int c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+    for (int x = 0; x < dim; ++x) {
+      c0[x] = max(0, (a[x] + n - 1) / n - 1 - ell);   // first centre whose box reaches the node
+      c1[x] = min(cP.N - 1, a[x] / n + ell);
+    }
+    double acc = 0.0;
+    int c[3];
+    for (c[2] = c0[2]; c[2] <= c1[2]; ++c[2])
+      for (c[1] = c0[1]; c[1] <= c1[1]; ++c[1])
+        for (c[0] = c0[0]; c[0] <= c1[0]; ++c[0]) {
+          const Geom g = make_geom_at(cP, c);
+          const int pid = (int)morton_encode(c, dim, cP.ref);
+          const int loc[3] = {a[0] - g.lo[0] * n, a[1] - g.lo[1] * n, a[2] - g.lo[2] * n};
+          const int li = node_index(g, loc) * s + comp;
+          for (int d = 0; d < s; ++d) acc += u[(size_t)pid * s + d] * phi[((size_t)pid * s + d) * nf_max + li];
+        }
+    u_fine[idx] = acc;
+  }
+}
+
+// Morton code of a cell by bit dilation (same value as morton_encode of geom.h, a dozen instructions instead of a loop
+// over dim * ref bits: the column index is computed for every entry of every matrix-vector product)
+__device__ __forceinline__ unsigned dilate2(unsigned x) {
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ unsigned dilate3(unsigned x) {
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__device__ __forceinline__ unsigned morton_fast(const int c[3], int dim) {
+  return (dim == 3) ? (dilate3(c[0]) | (dilate3(c[1]) << 1) | (dilate3(c[2]) << 2))
+                    : (dilate2(c[0]) | (dilate2(c[1]) << 1));
+}
+
+// ---- conjugate gradients on the block-ELL coarse matrix ----
+// Device-side scalars: the host only reads them back every few iterations.
+struct CgState {
+  double rz[2];      // r.z of the current / next iteration (index = iteration parity)
+  double rr0;        // ||r_0||^2
+  double rr;         // ||r||^2 after the last completed step
+  double tol2, red2; // squared absolute tolerance and squared reduction factor (ReductionControl)
+  int steps;         // completed steps
+  int done;          // 1: converged, 2: breakdown (p.Kp <= 0)
+};
+
+// x = 0, r = b, z = D^-1 r, p = z; one block (the vectors are short)
+__global__ void __launch_bounds__(1024)
+k_cg_init(int nrows, const double *__restrict__ Kell, const double *__restrict__ b, double *__restrict__ x,
+          double *__restrict__ r, double *__restrict__ p, double *__restrict__ dinv, CgState *st, double tol,
+          double reduction) {
+  __shared__ double sRed[32];
+  const int s = cP.s, w = cP.w, ww = 2 * w + 1;
+  const int centre = (cP.dim == 3) ? (w * ww + w) * ww + w : w * ww + w;
+  double rz = 0.0, rr = 0.0;
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    const int d = i % s;
+    const double diag = Kell[(size_t)i * cP.ell_width + centre * s + d];
+    const double di = 1.0 / diag;
+    const double ri = b[i];
+    dinv[i] = di;
+    x[i] = 0.0;
+    r[i] = ri;
+    p[i] = di * ri;
+    rz += ri * di * ri;
+    rr += ri * ri;
+  }
+  rz = block_sum(rz, sRed);
+  rr = block_sum(rr, sRed);
+  if (threadIdx.x == 0) {
+    st->rz[0] = rz;
+    st->rz[1] = 0.0;
+    st->rr0 = rr;
+    st->rr = rr;
+    st->tol2 = tol * tol;
+    st->red2 = reduction * reduction;
+    st->steps = 0;
+    st->done = (rr <= tol * tol) ? 1 : 0;
+  }
+}
+
+// q = K p, one warp per row; per-block partial sums of p.q
+__global__ void __launch_bounds__(kCgThreads)
+k_cg_spmv(int nrows, const double *__restrict__ Kell, const double *__restrict__ p, double *__restrict__ q,
+          double *__restrict__ partial, const CgState *st) {
+  __shared__ double sRed[kCgThreads / 32];
+  if (st->done) return;
+  const int s = cP.s, w = cP.w, ww = 2 * w + 1, dim = cP.dim;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * (kCgThreads / 32) + warp;
+  double acc = 0.0;
+  if (row < nrows) {
+    const int pid = row / s;
+    int c[3];
+    morton_decode((uint32_t)pid, dim, cP.ref, c);
+    const double *kr = Kell + (size_t)row * cP.ell_width;
+    const float inv_ww = 1.0f / (float)ww;   // exact quotients for these small integers
+    for (int t = lane; t < cP.ell_width; t += 32) {
+      const int slot = (s == 1) ? t : (t >> 1), e = (s == 1) ? 0 : (t & 1);   // spacedim is 1 or 2
+      const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
+      int qc[3] = {c[0] + (slot - s1 * ww) - w, c[1] + (s1 - s2 * ww) - w, (dim == 3) ? c[2] + s2 - w : 0};
+      bool valid = true;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) if (x < dim) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
+      if (valid) acc += kr[t] * p[(size_t)morton_fast(qc, dim) * s + e];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) q[row] = acc;
+    acc *= p[row];
+  }
+  __syncthreads();
+  if (lane == 0) sRed[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kCgThreads / 32; ++i) t += sRed[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// alpha = r.z / p.Kp; x += alpha p; r -= alpha q; partial sums of r.D^-1 r and r.r
+__global__ void __launch_bounds__(kCgThreads)
+k_cg_update(int nrows, int it, const double *__restrict__ p, const double *__restrict__ q,
+            const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+            const double *__restrict__ partial_pq, int n_partial, double *__restrict__ partial_rz,
+            double *__restrict__ partial_rr, CgState *st) {
+  __shared__ double sRed[kCgThreads / 32];
+  if (st->done) return;
+  const double pq = array_sum(partial_pq, n_partial, sRed);
+  const double alpha = st->rz[it & 1] / pq;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0.0, rr = 0.0;
+  if (i < nrows && pq > 0.0) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    rz = ri * dinv[i] * ri;
+    rr = ri * ri;
+  }
+  rz = block_sum(rz, sRed);
+  rr = block_sum(rr, sRed);
+  if (threadIdx.x == 0) {
+    partial_rz[blockIdx.x] = (pq > 0.0) ? rz : -1.0;   // a negative entry flags the breakdown to k_cg_direction
+    partial_rr[blockIdx.x] = rr;
+  }
+}
+
+// beta = r'.z' / r.z; p = z' + beta p; block 0 records the step and the stopping test
+__global__ void __launch_bounds__(kCgThreads)
+k_cg_direction(int nrows, int it, const double *__restrict__ r, const double *__restrict__ dinv,
+               double *__restrict__ p, const double *__restrict__ partial_rz, const double *__restrict__ partial_rr,
+               int n_partial, CgState *st) {
+  __shared__ double sRed[kCgThreads / 32];
+  if (st->done) return;
+  const bool breakdown = partial_rz[0] < 0.0;
+  const double rz_new = array_sum(partial_rz, n_partial, sRed);
+  const double rr = array_sum(partial_rr, n_partial, sRed);
+  const double rz_old = st->rz[it & 1];
+  const double rr0 = st->rr0, tol2 = st->tol2, red2 = st->red2;
+  __syncthreads();   // every thread of block 0 has read the state before it is advanced
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!breakdown && i < nrows) p[i] = dinv[i] * r[i] + (rz_new / rz_old) * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (breakdown) {
+      st->done = 2;
+    } else {
+      st->rz[(it + 1) & 1] = rz_new;
+      st->rr = rr;
+      st->steps = it + 1;
+      if (rr <= tol2 || rr <= red2 * rr0) st->done = 1;
+    }
+  }
+}
+
+}  // namespace slod

@@ -11,8 +11,9 @@
 // (source/LOD.cc:860-973), are calls into the C ABI of libslod_b200.so (include/slod.h); everything the reference
 // builds per patch on the host (Triangulation, DoFHandler, sparsity patterns, index vectors) is closed-form index
 // arithmetic inside that library, so the host keeps only the parameter interface, the coefficient tables and the
-// results.  Stages after assemble_global_matrix (fine FEM solve, coarse solve, error tables, VTU) are out of scope
-//  and are not run.
+// results.  After the offline phase run() also does SURVEY.md section 8f row 1 through the same handle: fine right-hand
+// side (constant forcing), solve() = C^T f + coarse CG, and the prolongation C u.  The fine FEM reference solve, the
+// error tables and the VTU writers (section 8f rows 2-3) are out of scope and are not run.
 //
 // Error behaviour: like the reference (AssertThrow -> exception -> main prints and returns 1), every failing C ABI
 // call becomes a std::runtime_error carrying slod_last_error().
@@ -21,6 +22,7 @@
 #include <slod.h>
 
 #include <chrono>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -171,6 +173,12 @@ public:
     prm.declare(P + "/Coefficients", "Maximum value for random coefficients", "100");                        // [+]
     prm.declare(P + "/Coefficients", "Refinement for random coefficients", spacedim == 1 ? (dim == 2 ? "8" : "6") : "6");  // [+]
     prm.declare(P + "/Coefficients", "Random seed", "0");  // [+] 0: unseeded rand() like the reference
+    // ParsedFunction (include/LOD.h:104,123): components separated by ';'.  This host evaluates constants only.
+    prm.declare(P + "/Right hand side", "Function expression", spacedim == 1 ? "0" : "0; 0");
+    // ReductionControl (include/LOD.h:109,127) with deal.II's defaults
+    prm.declare(P + "/Solver/Coarse solver control", "Max steps", "100");
+    prm.declare(P + "/Solver/Coarse solver control", "Tolerance", "1e-10");
+    prm.declare(P + "/Solver/Coarse solver control", "Reduction", "1e-2");
     prm.declare(P + "/B200", "Device", "-1");              // [+] CUDA device ordinal, -1 = current
     prm.declare(P + "/B200", "Write coarse matrix", "true");
   }
@@ -192,8 +200,13 @@ public:
     random_value_refinement =
         (unsigned)nonneg(prm.get_integer(P + "/Coefficients", "Refinement for random coefficients"), "Refinement");
     random_seed = (unsigned)nonneg(prm.get_integer(P + "/Coefficients", "Random seed"), "Random seed");
+    rhs_expression = prm.get(P + "/Right hand side", "Function expression");
+    coarse_max_steps = (unsigned)nonneg(prm.get_integer(P + "/Solver/Coarse solver control", "Max steps"), "Max steps");
+    coarse_tolerance = prm.get_double(P + "/Solver/Coarse solver control", "Tolerance");
+    coarse_reduction = prm.get_double(P + "/Solver/Coarse solver control", "Reduction");
     device = (int)prm.get_integer(P + "/B200", "Device");
     write_coarse_matrix = prm.get_bool(P + "/B200", "Write coarse matrix");
+    (void)rhs_constants();   // refuse what this host cannot evaluate before any work is done
   }
 
   std::string output_directory = ".";
@@ -208,8 +221,36 @@ public:
   double random_value_max = 100;
   unsigned int random_value_refinement = 8;
   unsigned int random_seed = 0;
+  std::string rhs_expression = spacedim == 1 ? "0" : "0; 0";
+  unsigned int coarse_max_steps = 100;
+  double coarse_tolerance = 1e-10, coarse_reduction = 1e-2;
   int device = -1;
   bool write_coarse_matrix = true;
+
+  // the constant value of every component of the right-hand side; anything but numbers is refused
+  std::vector<double> rhs_constants() const {
+    std::vector<double> v;
+    std::stringstream ss(rhs_expression);
+    std::string item;
+    while (std::getline(ss, item, ';')) {
+      size_t used = 0;
+      double x = 0;
+      try {
+        x = std::stod(item, &used);
+      } catch (const std::exception &) {
+        used = 0;
+      }
+      while (used < item.size() && std::isspace((unsigned char)item[used])) ++used;
+      if (used == 0 || used != item.size())
+        throw std::runtime_error("parameter <Function expression> of the right-hand side: only constant expressions are "
+                                 "evaluated by this host, got '" + item + "'");
+      v.push_back(x);
+    }
+    if ((int)v.size() != spacedim)
+      throw std::runtime_error("parameter <Function expression> of the right-hand side needs " +
+                               std::to_string(spacedim) + " components");
+    return v;
+  }
 
   mutable ParameterHandler prm;
 
@@ -331,13 +372,18 @@ public:
     create_random_problem_coefficients();
     compute_basis_function_candidates();
     assemble_global_matrix();
-    // assemble_and_solve_fem_problem / solve / compare_lod_with_fem / output_*: not part of the offline phase
+    assemble_fem_rhs();
+    solve();
+    prolongate_lod_solution();
+    // the fine FEM solve of assemble_and_solve_fem_problem, the error tables and the VTU writers are out of scope
     output_offline_results();
     computing_timer.print_summary(pcout);
   }
 
   const CoarseMatrix &get_global_stiffness_matrix() const { return global_stiffness_matrix; }
   const std::vector<Patch<dim>> &get_patches() const { return patches; }
+  const std::vector<double> &get_solution() const { return solution; }
+  const std::vector<double> &get_lod_solution() const { return lod_solution; }
 
 protected:
   void check(int rc, const char *what) const {
@@ -455,6 +501,60 @@ protected:
           "slod_get_coarse_csr");
   }
 
+  // The right-hand side half of assemble_and_solve_fem_problem (source/LOD.cc:1004-1040): F_i = int f phi_i with zero
+  // rows on the domain boundary.  For a constant f the Gauss sums (include/Diffusion.h:188-191) are the tensor product
+  // of the 1-D weights h (interior node) -- evaluated here on the host, it is mesh set-up, not patch work.
+  void assemble_fem_rhs() {
+    const std::vector<double> f = par.rhs_constants();
+    const size_t G = ((size_t)par.n_subdivisions << par.n_global_refinements) + 1;
+    const double h = 1.0 / (double)(G - 1);
+    fem_rhs.assign(n_dofs_fine, 0.0);
+    size_t nodes = 1;
+    for (int a = 0; a < dim; ++a) nodes *= G;
+    for (size_t node = 0; node < nodes; ++node) {
+      size_t r = node;
+      double w = 1.0;
+      for (int a = 0; a < dim; ++a) {
+        const size_t i = r % G;
+        r /= G;
+        w *= (i == 0 || i == G - 1) ? 0.0 : h;
+      }
+      for (int c = 0; c < spacedim; ++c) fem_rhs[node * spacedim + c] = w * f[c];
+    }
+    double nrm = 0;
+    for (double v : fem_rhs) nrm += v * v;
+    pcout << "     fem rhs l2 norm = " << std::sqrt(nrm) << std::endl;   // source/LOD.cc:1039
+  }
+
+  void solve() {  // source/LOD.cc:975-1001
+    TimerOutput::Scope t(computing_timer, "4: Solve LOD (B200)");
+    system_rhs.assign(n_dofs_coarse, 0.0);
+    solution.assign(n_dofs_coarse, 0.0);
+    check(slod_coarse_rhs(slod, fem_rhs.data(), system_rhs.data()), "slod_coarse_rhs");
+    double nrm = 0;
+    for (double v : system_rhs) nrm += v * v;
+    pcout << "     rhs l2 norm = " << std::sqrt(nrm) << std::endl;
+    int32_t steps = 0;
+    double residual = 0;
+    check(slod_coarse_solve(slod, system_rhs.data(), solution.data(), (int32_t)par.coarse_max_steps,
+                            par.coarse_tolerance, par.coarse_reduction, &steps, &residual),
+          "slod_coarse_solve");
+    pcout << "   size of u " << solution.size() << std::endl;
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "   coarse CG: %d steps, residual %.3e", (int)steps, residual);
+    pcout << buf << std::endl;
+  }
+
+  void prolongate_lod_solution() {  // first lines of compare_lod_with_fem, source/LOD.cc:1247-1251
+    lod_solution.assign(n_dofs_fine, 0.0);
+    check(slod_prolongate(slod, solution.data(), lod_solution.data()), "slod_prolongate");
+    double nrm = 0;
+    for (double v : lod_solution) nrm += v * v;
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "   lod solution l2 norm = %.12e", std::sqrt(nrm));
+    pcout << buf << std::endl;
+  }
+
   void output_offline_results() {
     const auto &K = global_stiffness_matrix;
     char buf[256];
@@ -486,6 +586,7 @@ protected:
   size_t n_dofs_coarse = 0, n_dofs_fine = 0;
   std::vector<Patch<dim>> patches;
   CoarseMatrix global_stiffness_matrix;
+  std::vector<double> fem_rhs, system_rhs, solution, lod_solution;   // include/LOD.h:236-239, lexicographic fine numbering
 };
 
 // include/Diffusion.h:56-306.  The reference draws Alpha(1,100,8) in the constructor; here the table is drawn in

@@ -113,6 +113,23 @@ int slod_assemble_coarse(slod_ctx *ctx);
 int slod_get_coarse_csr(const slod_ctx *ctx, int64_t *rowptr, int64_t *col, double *val, int64_t *n_rows,
                         int64_t *nnz);
 
+/* ---- online phase on the handle's basis and coarse matrix (replaces LOD::solve(),
+ * source/LOD.cc:975-1001, and the prolongation in LOD::compare_lod_with_fem(), source/LOD.cc:1251).
+ * Fine vectors are lexicographic: index = node * spacedim + component, node = x + G (y + G z), G = N n + 1 nodes per
+ * axis; slod_get_patch_fine_dofs gives the deal.II numbering of the same nodes.  Coarse vectors: spacedim*patch + comp. */
+int slod_fine_size(const slod_ctx *ctx, int64_t *n_fine);
+/* system_rhs = C^T fem_rhs  (basis_matrix_transposed.Tvmult(system_rhs, fem_rhs), source/LOD.cc:981). */
+int slod_coarse_rhs(slod_ctx *ctx, const double *f_fine, double *rhs_coarse);
+/* K u = rhs by conjugate gradients from u = 0 (SolverCG, source/LOD.cc:994-998), stopped like deal.II's
+ * ReductionControl ("Coarse solver control", include/LOD.h:109): ||r||_2 <= tolerance or ||r||_2 <= reduction * ||r_0||_2.
+ * Not converged within max_steps -> SLOD_ERR_NUMERIC (deal.II throws SolverControl::NoConvergence).  The preconditioner
+ * is diag(K), not the reference's SSOR(1.2): same solution to the tolerance, different step counts.
+ * steps / residual (may be NULL) receive the number of steps taken and the final ||r||_2. */
+int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse, int32_t max_steps, double tolerance,
+                      double reduction, int32_t *steps, double *residual);
+/* lod_solution = C u  (basis_matrix_transposed.vmult(lod_solution, solution), source/LOD.cc:1251). */
+int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine);
+
 /* Page-locked host memory for the caller-owned output buffers of slod_get_all_basis / slod_get_coarse_csr: copies
  * into pageable memory work too but run at a fraction of the link speed.  No reference counterpart. */
 int slod_alloc_host(size_t bytes, void **out);

@@ -15,6 +15,7 @@ paths relative to the reference root):
 * ``problem_parameter``                        include/Diffusion.h:7-54
 * ``LOD::compute_basis_function_candidates``   source/LOD.cc:296-768
 * ``LOD::assemble_global_matrix``              source/LOD.cc:860-973
+* ``LOD::solve`` (+ fine rhs, prolongation)    source/LOD.cc:975-1001, :1251, include/Diffusion.h:149-153,188-191
 
 deal.II 9.6 / Trilinos / LAPACK (the third-party libraries that carry the arithmetic) are not
 available in this environment, so the reference itself cannot be built; the oracle is pinned
@@ -652,6 +653,76 @@ class SlodOracle:
         for _ in range(pr.dim - 1):
             rhs = np.multiply.outer(w1, rhs)
         return rhs.ravel()
+
+
+    def fem_rhs(self, fn):
+        """Fine right-hand side F_i = int f phi_i with QIterated(QGauss<1>(2), n) per coarse cell, i.e. 2^dim Gauss
+        points per sub-cell (include/Diffusion.h:149-153, 188-191; the elasticity loop include/Elasticity.h:262-270 is
+        the same per component), rows on the domain boundary constrained to 0 (source/LOD.cc:1021-1027).
+        ``fn(points[npts, dim]) -> values[npts, spacedim]``.  Lexicographic numbering node * spacedim + comp."""
+        pr = self.prob
+        dim, s, h = pr.dim, pr.spacedim, pr.h
+        M = pr.N * pr.n_subdivisions
+        G = M + 1
+        t = 0.5 - 0.5 / math.sqrt(3.0)
+        gp = np.array([t, 1.0 - t])                 # Gauss points of the unit interval, weights 1/2 each
+        F = np.zeros((G,) * dim + (s,))             # indexed [z][y][x][comp] (x fastest in the flattened order)
+        cells = np.stack(np.meshgrid(*[np.arange(M)] * dim, indexing="ij"), axis=-1).reshape(-1, dim)  # (x, y, z)
+        for q in itertools.product(range(2), repeat=dim):
+            pts = (cells + gp[list(q)]) * h
+            val = np.asarray(fn(pts), dtype=float).reshape(len(pts), s) * (h / 2.0) ** dim
+            for loc in itertools.product(range(2), repeat=dim):
+                shape = np.ones(())
+                for a in range(dim):
+                    shape = shape * (gp[q[a]] if loc[a] == 1 else 1.0 - gp[q[a]])
+                idx = tuple((cells[:, a] + loc[a]) for a in reversed(range(dim)))
+                np.add.at(F, idx, val * shape)
+        for a in range(dim):                         # homogeneous Dirichlet rows
+            sl = [slice(None)] * (dim + 1)
+            for end in (0, G - 1):
+                sl[dim - 1 - a] = end
+                F[tuple(sl)] = 0.0
+        return F.reshape(-1)
+
+    # -- LOD::solve (source/LOD.cc:975-1001) and the prolongation (source/LOD.cc:1251) -----------------------------
+    @staticmethod
+    def solve_coarse(K, b, max_steps=100, tolerance=1e-10, reduction=1e-10, omega=1.2, direct=False):
+        """CG preconditioned with one SSOR(omega = 1.2) sweep, stopped by deal.II's ReductionControl
+        (||r|| <= tolerance or ||r|| <= reduction ||r_0||); ``direct=True`` is the reference's debugging branch
+        (SolverDirect, source/LOD.cc:984-989).  Returns (u, steps)."""
+        K = sp.csr_matrix(K)
+        b = np.asarray(b, dtype=float)
+        if direct:
+            return spla.spsolve(K.tocsc(), b), 0
+        D = K.diagonal()
+        Lw = (sp.tril(K, -1) * omega + sp.diags(D)).tocsr()
+        Uw = (sp.triu(K, 1) * omega + sp.diags(D)).tocsr()
+
+        def prec(r):   # (D + w L)^-1 ... D ... (D + w U)^-1, scaled by w (2 - w)
+            y = spla.spsolve_triangular(Lw, r, lower=True)
+            return omega * (2.0 - omega) * spla.spsolve_triangular(Uw, D * y, lower=False)
+
+        u = np.zeros_like(b)
+        r = b.copy()
+        r0 = np.linalg.norm(r)
+        if r0 <= tolerance:
+            return u, 0
+        z = prec(r)
+        p = z.copy()
+        rz = r @ z
+        for it in range(1, max_steps + 1):
+            q = K @ p
+            alpha = rz / (p @ q)
+            u += alpha * p
+            r -= alpha * q
+            res = np.linalg.norm(r)
+            if res <= tolerance or res <= reduction * r0:
+                return u, it
+            z = prec(r)
+            rz_new = r @ z
+            p = z + (rz_new / rz) * p
+            rz = rz_new
+        raise RuntimeError(f"SolverControl::NoConvergence after {max_steps} steps, residual {res:.3e}")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -21,6 +21,16 @@ PRM = """subsection Problem
     set Refinement for random coefficients = {r}
     set Random seed = {seed}
   end
+  subsection Right hand side
+    set Function expression = {rhs}
+  end
+  subsection Solver
+    subsection Coarse solver control
+      set Max steps = 2000
+      set Tolerance = 0
+      set Reduction = 1e-12
+    end
+  end
 end
 """
 
@@ -48,9 +58,10 @@ def test_template_prm_and_no_cpu_fallback(apps, tmp_path):
     prm = (tmp_path / "parameters.prm").read_text()   # ParameterAcceptor writes a template when the file is missing
     for key in ("Output directory", "Output name", "Oversampling", "Number of subdivisions",
                 "Number of global refinements", "Compare with fine global solution", "Stabilize phi_LOD candidates",
-                "Constant problem coefficients"):
+                "Constant problem coefficients", "Function expression", "Max steps", "Tolerance", "Reduction"):
         assert f"set {key} = " in prm                   # include/LOD.h:133-143
     assert "subsection Problem" in prm and "subsection Coefficients" in prm
+    assert "subsection Right hand side" in prm and "subsection Coarse solver control" in prm   # include/LOD.h:123,127
     used = (tmp_path / "used_parameters_2.prm").read_text()   # source/LOD.cc:60-62
     assert "set Oversampling = 1" in used
 
@@ -62,6 +73,12 @@ def test_prm_errors(apps, tmp_path):
     (tmp_path / "bad2.prm").write_text("subsection Problem\n  set Oversampling = two\nend\n")
     res = subprocess.run([apps["main_Diffusion3D"], "bad2.prm"], cwd=tmp_path, capture_output=True, text=True)
     assert res.returncode == 1 and "not an integer" in res.stderr
+    (tmp_path / "bad4.prm").write_text("subsection Problem\n  subsection Right hand side\n    set Function expression = sin(x)\n  end\nend\n")
+    res = subprocess.run([apps["main_Diffusion"], "bad4.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 1 and "only constant expressions" in res.stderr
+    (tmp_path / "bad5.prm").write_text("subsection Problem\n  subsection Right hand side\n    set Function expression = 1\n  end\nend\n")
+    res = subprocess.run([apps["main_Elasticity"], "bad5.prm"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 1 and "needs 2 components" in res.stderr
     (tmp_path / "bad3.prm").write_text("subsection Problem\n  set Oversampling = 1\n")
     res = subprocess.run([apps["main_Diffusion"], "bad3.prm"], cwd=tmp_path, capture_output=True, text=True)
     assert res.returncode == 1 and "unterminated subsection" in res.stderr
@@ -85,7 +102,8 @@ def _read_matrix(path):
 def test_apps_match_oracle(apps, tmp_path, app, dim, s, ref, ell, r):
     from oracle.slod_oracle import CoefficientTable, GlibcRand, SlodOracle, SlodProblem, reference_random_table
     seed = 5
-    (tmp_path / "p.prm").write_text(PRM.format(ell=ell, ref=ref, r=r, seed=seed))
+    rhs = [1.0] if s == 1 else [1.0, -0.5]
+    (tmp_path / "p.prm").write_text(PRM.format(ell=ell, ref=ref, r=r, seed=seed, rhs="; ".join(str(v) for v in rhs)))
     res = subprocess.run([apps[app], "p.prm"], cwd=tmp_path, capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert f"Number of patches = {(2 ** ref) ** dim}" in res.stdout
@@ -99,3 +117,15 @@ def test_apps_match_oracle(apps, tmp_path, app, dim, s, ref, ell, r):
     K, _, _ = orc.assemble_global_matrix()
     assert np.array_equal(rowptr, K.indptr) and np.array_equal(col, K.indices)
     assert np.abs(val - K.data).max() <= 1e-8 * np.abs(K.data).max()
+    # online stages (LOD::solve, source/LOD.cc:975-1001; prolongation :1251) as printed by the host
+    import re
+    _, C, _ = orc.assemble_global_matrix()
+    f = orc.fem_rhs(lambda p: np.tile(rhs, (len(p), 1)))
+    out = res.stdout
+    assert abs(float(re.search(r"fem rhs l2 norm = (\S+)", out).group(1)) - np.linalg.norm(f)) <= 1e-5 * np.linalg.norm(f)
+    b = C.T @ f
+    assert abs(float(re.search(r"\n\s+rhs l2 norm = (\S+)", out).group(1)) - np.linalg.norm(b)) <= 1e-5 * np.linalg.norm(b)
+    assert f"size of u {s * (2 ** ref) ** dim}" in out
+    u, _ = orc.solve_coarse(K, b, direct=True)
+    nrm = float(re.search(r"lod solution l2 norm = (\S+)", out).group(1))
+    assert abs(nrm - np.linalg.norm(C @ u)) <= 1e-7 * np.linalg.norm(C @ u)

@@ -119,6 +119,27 @@ def test_poisson_lod_example(golden_dir):
     assert K.shape == (16, 16)
 
 
+def test_online_restatement_consistency():
+    """fem_rhs (Gauss quadrature) reproduces the closed form for f = 1 and integrates a linear f exactly; the oracle's
+    CG + SSOR(1.2) (LOD::solve, source/LOD.cc:991-998) agrees with the direct branch (source/LOD.cc:984-989)."""
+    prob = SlodProblem(dim=2, spacedim=1, n_global_refinements=3, n_subdivisions=2, oversampling=1, stabilize=True,
+                       coefficients=[CoefficientTable(2, 4, 1.0 + 99.0 * np.random.default_rng(5).random(256))])
+    o = SlodOracle(prob)
+    assert np.abs(o.fem_rhs(lambda p: np.ones((len(p), 1))) - o.fem_rhs_constant_one()).max() < 1e-16
+    F = o.fem_rhs(lambda p: p[:, [0]] + 2.0 * p[:, [1]]).reshape(17, 17)     # [y][x]
+    assert abs(F[5, 3] - (3 / 16 + 2 * 5 / 16) * (1 / 16) ** 2) < 1e-16        # interior node: f(node) h^2
+    assert not F[0].any() and not F[:, -1].any()                              # constrained rows
+    o.compute_basis()
+    K, C, _ = o.assemble_global_matrix()
+    b = C.T @ o.fem_rhs(lambda p: np.sin(3 * p[:, [0]]) + p[:, [1]])
+    u_cg, steps = o.solve_coarse(K, b, max_steps=500, tolerance=0.0, reduction=1e-12)
+    u_direct, _ = o.solve_coarse(K, b, direct=True)
+    assert 0 < steps < 500
+    assert np.linalg.norm(u_cg - u_direct) <= 1e-9 * np.linalg.norm(u_direct)
+    with pytest.raises(RuntimeError):
+        o.solve_coarse(K, b, max_steps=1, tolerance=0.0, reduction=1e-12)
+
+
 def test_assembly_02_frobenius(golden_dir):
     """tests/assembly_02.cc: 1-D, 5 coarse cells x 2 sub-cells, indicator basis: C^T A C has 20 on the
     diagonal and four 10s coupling... -> Frobenius norm 48.9898 (hand-checked in SURVEY 4.2)."""
