@@ -1018,8 +1018,13 @@ cudaError_t launch_prolongate(cudaStream_t st, long long n_fine, const double *p
   k_prolongate<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), kCgThreads, 0, st>>>(n_fine, phi, u, u_fine, nf_max);
   return cudaGetLastError();
 }
+// a few waves of persistent blocks: short partial-sum arrays for the two vector kernels to reduce
+static int cg_spmv_blocks(int nrows) {
+  const int per = kCgThreads / 32, want = (nrows + per - 1) / per;
+  return want < 148 * 8 ? want : 148 * 8;
+}
 size_t cg_workspace_doubles(int nrows) {
-  const int nb_spmv = (nrows + kCgThreads / 32 - 1) / (kCgThreads / 32), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+  const int nb_spmv = cg_spmv_blocks(nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
   // r, p, q, dinv | partial p.q | partial r.z, r.r | state
   return (size_t)4 * nrows + nb_spmv + 2 * (size_t)nb_vec + (sizeof(CgState) + 7) / 8;
 }
@@ -1028,8 +1033,7 @@ size_t cg_workspace_doubles(int nrows) {
 cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const double *b, double *x, double *work,
                           int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
                           long long *launches) {
-  const int per = kCgThreads / 32;
-  const int nb_spmv = (nrows + per - 1) / per, nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+  const int nb_spmv = cg_spmv_blocks(nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
   double *r = work, *p = r + nrows, *q = p + nrows, *dinv = q + nrows;
   double *ppq = dinv + nrows, *prz = ppq + nb_spmv, *prr = prz + nb_vec;
   CgState *state = reinterpret_cast<CgState *>(prr + nb_vec);

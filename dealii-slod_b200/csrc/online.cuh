@@ -165,37 +165,59 @@ k_cg_init(int nrows, const double *__restrict__ Kell, const double *__restrict__
   }
 }
 
-// q = K p, one warp per row; per-block partial sums of p.q
+// q = K p, one warp per row (grid-stride over row groups); per-block partial sums of p.q.
+// The column of entry (dx, dy, dz) is dilate(cx + dx) | dilate(cy + dy) << 1 | dilate(cz + dz) << 2: each warp tabulates
+// the 3 (2w+1) dilated coordinates of its row in shared memory (sign bit = outside the domain), so an entry costs three
+// table reads and two ORs, and the sweep is bound by the 8 bytes per entry it reads.
+constexpr int kCgTab = 32;   // 2w+1 <= 32 (oversampling <= 7); larger stencils take the direct path
 __global__ void __launch_bounds__(kCgThreads)
 k_cg_spmv(int nrows, const double *__restrict__ Kell, const double *__restrict__ p, double *__restrict__ q,
           double *__restrict__ partial, const CgState *st) {
   __shared__ double sRed[kCgThreads / 32];
+  __shared__ int sTab[kCgThreads / 32][3][kCgTab];
   if (st->done) return;
   const int s = cP.s, w = cP.w, ww = 2 * w + 1, dim = cP.dim;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * (kCgThreads / 32) + warp;
-  double acc = 0.0;
-  if (row < nrows) {
+  const bool tabulated = ww <= kCgTab;
+  const float inv_ww = 1.0f / (float)ww;   // exact quotients for these small integers
+  double pq = 0.0;
+  for (int row = blockIdx.x * (kCgThreads / 32) + warp; row < nrows; row += gridDim.x * (kCgThreads / 32)) {
     const int pid = row / s;
     int c[3];
     morton_decode((uint32_t)pid, dim, cP.ref, c);
     const double *kr = Kell + (size_t)row * cP.ell_width;
-    const float inv_ww = 1.0f / (float)ww;   // exact quotients for these small integers
-    for (int t = lane; t < cP.ell_width; t += 32) {
-      const int slot = (s == 1) ? t : (t >> 1), e = (s == 1) ? 0 : (t & 1);   // spacedim is 1 or 2
-      const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
-      int qc[3] = {c[0] + (slot - s1 * ww) - w, c[1] + (s1 - s2 * ww) - w, (dim == 3) ? c[2] + s2 - w : 0};
-      bool valid = true;
+    double acc = 0.0;
+    if (tabulated) {
+      __syncwarp();
+      for (int i = lane; i < 3 * ww; i += 32) {
+        const int a = i / ww, d = i - a * ww, v = c[a] + d - w;
+        int code = 0;
+        if (a < dim) code = (v >= 0 && v < cP.N) ? (int)(((dim == 3) ? dilate3(v) : dilate2(v)) << a) : (int)0x80000000;
+        sTab[warp][a][d] = code;
+      }
+      __syncwarp();
+      for (int t = lane; t < cP.ell_width; t += 32) {
+        const int slot = (s == 1) ? t : (t >> 1), e = (s == 1) ? 0 : (t & 1);   // spacedim is 1 or 2
+        const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
+        const int col = sTab[warp][0][slot - s1 * ww] | sTab[warp][1][s1 - s2 * ww] | sTab[warp][2][s2];
+        if (col >= 0) acc += kr[t] * p[(size_t)col * s + e];
+      }
+    } else {
+      for (int t = lane; t < cP.ell_width; t += 32) {
+        const int slot = (s == 1) ? t : (t >> 1), e = (s == 1) ? 0 : (t & 1);
+        const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
+        int qc[3] = {c[0] + (slot - s1 * ww) - w, c[1] + (s1 - s2 * ww) - w, (dim == 3) ? c[2] + s2 - w : 0};
+        bool valid = true;
 #pragma unroll
-      for (int x = 0; x < 3; ++x) if (x < dim) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
-      if (valid) acc += kr[t] * p[(size_t)morton_fast(qc, dim) * s + e];
+        for (int x = 0; x < 3; ++x) if (x < dim) valid = valid && (qc[x] >= 0 && qc[x] < cP.N);
+        if (valid) acc += kr[t] * p[(size_t)morton_fast(qc, dim) * s + e];
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) q[row] = acc;
-    acc *= p[row];
+    pq += acc * p[row];   // rows of a warp in ascending order: fixed summation order
   }
-  __syncthreads();
-  if (lane == 0) sRed[warp] = acc;
+  if (lane == 0) sRed[warp] = pq;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;

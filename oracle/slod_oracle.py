@@ -684,6 +684,19 @@ class SlodOracle:
                 F[tuple(sl)] = 0.0
         return F.reshape(-1)
 
+    def fem_solve(self, F):
+        """Fine-scale FEM solution of assemble_and_solve_fem_problem (source/LOD.cc:1004-1094): global Q_iso_Q1 stiffness
+        of the whole domain, homogeneous Dirichlet rows, right-hand side F (from fem_rhs).  Solved directly instead of
+        with the reference's CG + AMG.  Lexicographic numbering."""
+        pr = self.prob
+        whole = PatchShape(pr.dim, pr.spacedim, pr.n_subdivisions, (pr.N,) * pr.dim, (True,) * pr.dim, (True,) * pr.dim,
+                           (0,) * pr.dim)
+        A = self.assemble_patch_stiffness(whole, (0,) * pr.dim).tocsr()
+        ii = whole.internal
+        u = np.zeros(whole.Nf)
+        u[ii] = spla.spsolve(A[ii][:, ii].tocsc(), np.asarray(F, dtype=float)[ii])
+        return u, A
+
     # -- LOD::solve (source/LOD.cc:975-1001) and the prolongation (source/LOD.cc:1251) -----------------------------
     @staticmethod
     def solve_coarse(K, b, max_steps=100, tolerance=1e-10, reduction=1e-10, omega=1.2, direct=False):

@@ -143,6 +143,29 @@ def test_solution_against_oracle(case):
     ctx.close()
 
 
+@pytest.mark.parametrize("dim,s,ref,bounds", [
+    (2, 1, 4, [0.3, 6e-3, 2e-5]),      # measured on B200: 2.0e-1, 3.7e-3, 7.8e-6 (the oracle's own chain gives the same)
+    (2, 2, 3, [0.25, 7e-3]),           # 1.5e-1, 4.3e-3
+    (3, 1, 3, [0.15, 1e-3]),           # 9.1e-2, 6.2e-4
+    (3, 1, 4, [None, 3e-3]),           # ell = 2 only: 1.6e-3 (4096 patches of the cfg 4 shape)
+])
+def test_slod_solution_converges_to_fine_fem(dim, s, ref, bounds):
+    """The property the reference reports (error_LOD_FEMh, source/LOD.cc:1252) and the one check of the SLOD branch and of
+    the 3-D extension that needs no reference run: for a forcing that is constant on the coarse cells the SLOD solution
+    of the GPU chain differs from the fine-scale FEM solution only by the localization error, which decays
+    super-exponentially with the oversampling (profiles/r01_lod_vs_fem.txt)."""
+    from lod_vs_fem import lod_vs_fem
+    prev = None
+    for ell, bound in zip((1, 2, 3), bounds):
+        if bound is None:
+            continue
+        energy, l2, steps = lod_vs_fem(dim, s, ref, ell)
+        assert energy < bound and l2 < bound, (ell, energy, l2)
+        if prev is not None:
+            assert energy < prev / 20.0
+        prev = energy
+
+
 def test_poisson_lod_example_rhs_norm(golden_dir):
     """tests/Poisson_LOD_Example.output: `rhs l2 norm = 0.0808367`, `size of u 16` -- now computed by slod_coarse_rhs."""
     txt = open(os.path.join(golden_dir, "Poisson_LOD_Example.output")).read()
