@@ -49,14 +49,18 @@ k_coarse_rhs(int n_patches, const double *__restrict__ phi, const double *__rest
   const Geom g = make_geom(cP, pid);
   const int G = cP.nsub + 1;
   const double *pp = phi + (size_t)row * nf_max;
-  const int xs = g.p[0] * s;   // contiguous run: one x line of nodes with their components
+  const int xs = g.p[0] * s;        // one x line of nodes with their components is contiguous in both arrays
+  const int plane = xs * g.p[1];    // lanes sweep an (x, y) plane of the box, the z loop only adds strides
+  const double *f0 = f + (((size_t)(g.lo[2] * n) * G + g.lo[1] * n) * G + g.lo[0] * n) * s;
+  const size_t fz = (size_t)G * G * s;
   double acc = 0.0;
-  for (int z = 0; z < g.p[2]; ++z)
-    for (int y = 0; y < g.p[1]; ++y) {
-      const double *pl = pp + (size_t)(z * g.p[1] + y) * xs;
-      const double *fl = f + (((size_t)(g.lo[2] * n + z) * G + (g.lo[1] * n + y)) * G + g.lo[0] * n) * s;
-      for (int i = lane; i < xs; i += 32) acc += pl[i] * fl[i];
-    }
+  for (int t = lane; t < plane; t += 32) {
+    const int y = t / xs, x = t - y * xs;
+    const double *pl = pp + t;
+    const double *fl = f0 + (size_t)y * G * s + x;
+#pragma unroll 4
+    for (int z = 0; z < g.p[2]; ++z) acc += pl[(size_t)z * plane] * fl[z * fz];
+  }
   acc = warp_sum(acc);
   if (lane == 0) b[row] = acc;
 }
@@ -196,11 +200,26 @@ k_cg_spmv(int nrows, const double *__restrict__ Kell, const double *__restrict__
         sTab[warp][a][d] = code;
       }
       __syncwarp();
-      for (int t = lane; t < cP.ell_width; t += 32) {
-        const int slot = (s == 1) ? t : (t >> 1), e = (s == 1) ? 0 : (t & 1);   // spacedim is 1 or 2
-        const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
-        const int col = sTab[warp][0][slot - s1 * ww] | sTab[warp][1][s1 - s2 * ww] | sTab[warp][2][s2];
-        if (col >= 0) acc += kr[t] * p[(size_t)col * s + e];
+      for (int t0 = lane; t0 < cP.ell_width; t0 += 128) {   // four independent entries in flight per lane
+        double kv[4];
+        int col[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + 32 * u;
+          kv[u] = (t < cP.ell_width) ? __ldcs(kr + t) : 0.0;   // K is streamed once per sweep: keep p in the caches
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + 32 * u, tc = min(t, cP.ell_width - 1);   // clamped: table indices stay in range
+          const int slot = (s == 1) ? tc : (tc >> 1), e = (s == 1) ? 0 : (tc & 1);   // spacedim is 1 or 2
+          const int s1 = (int)(((float)slot + 0.5f) * inv_ww), s2 = (int)(((float)s1 + 0.5f) * inv_ww);
+          const int cc = (t < cP.ell_width)
+                             ? (sTab[warp][0][slot - s1 * ww] | sTab[warp][1][s1 - s2 * ww] | sTab[warp][2][s2]) : -1;
+          col[u] = (cc >= 0) ? cc * s + e : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (col[u] >= 0) acc += kv[u] * p[col[u]];
       }
     } else {
       for (int t = lane; t < cP.ell_width; t += 32) {
