@@ -27,6 +27,7 @@ EXPORTS = [
     "slod_get_patch_diagnostics", "slod_debug_patch_stages", "slod_get_timings", "slod_compute_basis_device",
     "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
     "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
+    "slod_fem_solve", "slod_fine_norms",
 ]
 
 
@@ -68,6 +69,8 @@ def load_library():
     lib.slod_coarse_rhs.argtypes = [vp, P(dbl), P(dbl)]
     lib.slod_coarse_solve.argtypes = [vp, P(dbl), P(dbl), i32, dbl, dbl, P(i32), P(dbl)]
     lib.slod_prolongate.argtypes = [vp, P(dbl), P(dbl)]
+    lib.slod_fem_solve.argtypes = [vp, P(dbl), P(dbl), i32, dbl, dbl, P(i32), P(dbl)]
+    lib.slod_fine_norms.argtypes = [vp, P(dbl), P(dbl), P(dbl), P(dbl)]
     lib.slod_get_patch_info.argtypes = [vp, i64] + [P(i32)] * 6 + [P(i32), P(i32)]
     lib.slod_get_patch_cells.argtypes = [vp, i64, P(C.c_uint32), P(i32)]
     lib.slod_get_patch_fine_dofs.argtypes = [vp, i64, P(C.c_uint64), P(i32)]
@@ -271,6 +274,27 @@ class SlodContext:
         out = np.empty(self.n_fine)
         self._ck(self.lib.slod_prolongate(self.h, _dp(u), _dp(out)))
         return out
+
+    # -- fine-scale reference problem (assemble_and_solve_fem_problem, source/LOD.cc:1004-1094) and norms (:1252) --
+    def fem_solve(self, f_fine, max_steps=200000, tolerance=1e-12, reduction=1e-10):
+        """Returns (u_fine, steps, residual)."""
+        f = np.ascontiguousarray(f_fine, dtype=np.float64).ravel()
+        if f.size != self.n_fine:
+            raise ValueError(f"fine vector has {f.size} entries, expected {self.n_fine}")
+        u = np.empty_like(f)
+        steps, res = C.c_int32(), C.c_double()
+        self._ck(self.lib.slod_fem_solve(self.h, _dp(f), _dp(u), max_steps, tolerance, reduction,
+                                         C.byref(steps), C.byref(res)))
+        return u, steps.value, res.value
+
+    def fine_norms(self, v_fine):
+        """(L2 norm, H1 seminorm, energy norm) of a fine vector."""
+        v = np.ascontiguousarray(v_fine, dtype=np.float64).ravel()
+        if v.size != self.n_fine:
+            raise ValueError(f"fine vector has {v.size} entries, expected {self.n_fine}")
+        l2, h1, en = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.slod_fine_norms(self.h, _dp(v), C.byref(l2), C.byref(h1), C.byref(en)))
+        return l2.value, h1.value, en.value
 
     def diagnostics(self, patch, comp=0):
         out = np.empty(8)

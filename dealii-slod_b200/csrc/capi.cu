@@ -1129,13 +1129,14 @@ int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse,
   double *d_b = nullptr, *d_x = nullptr, *d_work = nullptr;
   CK(cudaMalloc(&d_b, sizeof(double) * 2 * (size_t)nrows));
   d_x = d_b + nrows;
-  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(nrows));
+  const CgOperator A{ctx->d_Kell, nullptr, 0};
+  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(A, nrows));
   int st_steps = 0, flag = 0;
   long long n_launch = 0;
   double res = 0.0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, rhs_coarse, sizeof(double) * nrows, cudaMemcpyHostToDevice, 0);
   if (e == cudaSuccess)
-    e = run_coarse_cg(0, nrows, ctx->d_Kell, d_b, d_x, d_work, max_steps, tolerance, reduction, &st_steps, &res, &flag,
+    e = run_cg(0, nrows, A, d_b, d_x, d_work, max_steps, tolerance, reduction, &st_steps, &res, &flag,
                       &n_launch);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u_coarse, d_x, sizeof(double) * nrows, cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
@@ -1175,6 +1176,101 @@ int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine) {
   cudaFree(d_f);
   ctx->launches += 1;
   if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_prolongate: ") + cudaGetErrorString(e));
+  return SLOD_OK;
+}
+
+// ---- fine-scale reference problem and norms ----
+int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t max_steps, double tolerance,
+                   double reduction, int32_t *steps, double *residual) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!f_fine || !u_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  if (max_steps < 0 || !(tolerance >= 0.0) || !(reduction >= 0.0))
+    return fail(ctx, SLOD_ERR_INVALID, "solver control: max_steps, tolerance and reduction must be non-negative");
+  CK(cudaSetDevice(ctx->device));
+  int rc = prepare_coefficients(ctx);
+  if (rc) return rc;
+  CK(upload_params(ctx->P));
+  const Params &P = ctx->P;
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const long long n_nodes = n_fine / P.s;
+  // homogeneous Dirichlet conditions: the boundary rows of the right-hand side are constrained away (source/LOD.cc:1021-1027)
+  std::vector<double> f(f_fine, f_fine + n_fine);
+  const long long G = P.nsub + 1;
+  for (long long node = 0; node < n_nodes; ++node) {
+    long long r = node;
+    bool bd = false;
+    for (int a = 0; a < P.dim; ++a) {
+      const long long i = r % G;
+      r /= G;
+      bd = bd || i == 0 || i == G - 1;
+    }
+    if (bd)
+      for (int c = 0; c < P.s; ++c) f[node * P.s + c] = 0.0;
+  }
+  const CgOperator A{nullptr, ctx->d_coef, n_nodes};
+  double *d_b = nullptr, *d_work = nullptr;
+  CK(cudaMalloc(&d_b, sizeof(double) * 2 * (size_t)n_fine));
+  double *d_x = d_b + n_fine;
+  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(A, (int)n_fine));
+  int st_steps = 0, flag = 0;
+  long long n_launch = 0;
+  double res = 0.0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, f.data(), sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess)
+    e = run_cg(0, (int)n_fine, A, d_b, d_x, d_work, max_steps, tolerance, reduction, &st_steps, &res, &flag, &n_launch);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(u_fine, d_x, sizeof(double) * (size_t)n_fine, cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_b);
+  cudaFree(d_work);
+  ctx->launches += n_launch;
+  if (steps) *steps = st_steps;
+  if (residual) *residual = res;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_fem_solve: ") + cudaGetErrorString(e));
+  if (flag == 2) return fail(ctx, SLOD_ERR_NUMERIC, "fine CG broke down: the stiffness operator is not positive definite");
+  if (flag != 1) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "fine CG did not converge: %d steps, residual %.3e", st_steps, res);
+    return fail(ctx, SLOD_ERR_NUMERIC, buf);
+  }
+  return SLOD_OK;
+}
+
+int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_semi, double *energy) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!v_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  int rc = prepare_coefficients(ctx);
+  if (rc) return rc;
+  CK(upload_params(ctx->P));
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const long long n_nodes = n_fine / ctx->P.s;
+  int nb = 0;
+  launch_fine_quadratic_form(0, kFineMass, n_nodes, nullptr, nullptr, nullptr, &nb);
+  double *d_v = nullptr, *d_part = nullptr;
+  CK(cudaMalloc(&d_v, sizeof(double) * (size_t)n_fine));
+  cudaError_t e = cudaMalloc(&d_part, sizeof(double) * 3 * (size_t)nb);
+  std::vector<double> part(3 * (size_t)nb);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, v_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
+  const int ops[3] = {kFineMass, kFineLaplace, kFineEnergy};
+  for (int k = 0; k < 3 && e == cudaSuccess; ++k)
+    e = launch_fine_quadratic_form(0, ops[k], n_nodes, ctx->d_coef, d_v, d_part + (size_t)k * nb, &nb);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_v);
+  cudaFree(d_part);
+  ctx->launches += 3;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_fine_norms: ") + cudaGetErrorString(e));
+  double sum[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k)
+    for (int i = 0; i < nb; ++i) sum[k] += part[(size_t)k * nb + i];   // block order: reproducible
+  if (l2) *l2 = std::sqrt(std::max(sum[0], 0.0));
+  if (h1_semi) *h1_semi = std::sqrt(std::max(sum[1], 0.0));
+  if (energy) *energy = std::sqrt(std::max(sum[2], 0.0));
   return SLOD_OK;
 }
 

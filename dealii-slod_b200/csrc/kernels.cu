@@ -1019,29 +1019,36 @@ cudaError_t launch_prolongate(cudaStream_t st, long long n_fine, const double *p
   return cudaGetLastError();
 }
 // a few waves of persistent blocks: short partial-sum arrays for the two vector kernels to reduce
-static int cg_spmv_blocks(int nrows) {
+static int cg_apply_blocks(const CgOperator &A, int nrows) {
+  if (!A.Kell) return (int)((A.n_nodes + kCgThreads - 1) / kCgThreads);   // fine operator: one thread per node
   const int per = kCgThreads / 32, want = (nrows + per - 1) / per;
   return want < 148 * 8 ? want : 148 * 8;
 }
-size_t cg_workspace_doubles(int nrows) {
-  const int nb_spmv = cg_spmv_blocks(nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+size_t cg_workspace_doubles(const CgOperator &A, int nrows) {
+  const int nb_apply = cg_apply_blocks(A, nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
   // r, p, q, dinv | partial p.q | partial r.z, r.r | state
-  return (size_t)4 * nrows + nb_spmv + 2 * (size_t)nb_vec + (sizeof(CgState) + 7) / 8;
+  return (size_t)4 * nrows + nb_apply + 2 * (size_t)nb_vec + (sizeof(CgState) + 7) / 8;
 }
-// Runs preconditioned CG until the device-side stopping test fires or max_steps is reached; the host looks at the
-// state every `check_every` steps (one 64-byte copy).  Returns the state in *steps / *residual / *flag.
-cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const double *b, double *x, double *work,
-                          int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
-                          long long *launches) {
-  const int nb_spmv = cg_spmv_blocks(nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
+// Runs diag-preconditioned CG until the device-side stopping test fires or max_steps is reached; the host looks at the
+// state every `check_every` steps (one 64-byte copy).  A.Kell != nullptr: block-ELL coarse matrix; else the fine
+// Dirichlet stiffness operator applied matrix free.  Returns the state in *steps / *residual / *flag.
+cudaError_t run_cg(cudaStream_t st, int nrows, const CgOperator &A, const double *b, double *x, double *work,
+                   int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
+                   long long *launches) {
+  const int nb_apply = cg_apply_blocks(A, nrows), nb_vec = (nrows + kCgThreads - 1) / kCgThreads;
   double *r = work, *p = r + nrows, *q = p + nrows, *dinv = q + nrows;
-  double *ppq = dinv + nrows, *prz = ppq + nb_spmv, *prr = prz + nb_vec;
+  double *ppq = dinv + nrows, *prz = ppq + nb_apply, *prr = prz + nb_vec;
   CgState *state = reinterpret_cast<CgState *>(prr + nb_vec);
   CgState h{};
   cudaError_t e;
-  k_cg_init<<<1, 1024, 0, st>>>(nrows, Kell, b, x, r, p, dinv, state, tol, reduction);
+  if (!A.Kell) {
+    k_fine_apply<<<nb_apply, kCgThreads, 0, st>>>(kFineStiffDirichlet, A.n_nodes, A.d_coef, nullptr, nullptr, dinv, nullptr,
+                                                 nullptr);
+    *launches += 1;
+  }
+  k_cg_init<<<1, 1024, 0, st>>>(nrows, A.Kell, b, x, r, p, dinv, state, tol, reduction);
   *launches += 1;
-  const int check_every = 16;
+  const int check_every = A.Kell ? 16 : 64;
   int it = 0;
   for (;;) {
     if ((e = cudaMemcpyAsync(&h, state, sizeof(CgState), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
@@ -1049,8 +1056,11 @@ cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const 
     if (h.done || it >= max_steps) break;
     const int upto = (it + check_every < max_steps) ? it + check_every : max_steps;
     for (; it < upto; ++it) {
-      k_cg_spmv<<<nb_spmv, kCgThreads, 0, st>>>(nrows, Kell, p, q, ppq, state);
-      k_cg_update<<<nb_vec, kCgThreads, 0, st>>>(nrows, it, p, q, dinv, x, r, ppq, nb_spmv, prz, prr, state);
+      if (A.Kell)
+        k_cg_spmv<<<nb_apply, kCgThreads, 0, st>>>(nrows, A.Kell, p, q, ppq, state);
+      else
+        k_fine_apply<<<nb_apply, kCgThreads, 0, st>>>(kFineStiffDirichlet, A.n_nodes, A.d_coef, p, q, nullptr, ppq, state);
+      k_cg_update<<<nb_vec, kCgThreads, 0, st>>>(nrows, it, p, q, dinv, x, r, ppq, nb_apply, prz, prr, state);
       k_cg_direction<<<nb_vec, kCgThreads, 0, st>>>(nrows, it, r, dinv, p, prz, prr, nb_vec, state);
       *launches += 3;
     }
@@ -1059,6 +1069,14 @@ cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const 
   *steps = h.steps;
   *residual = sqrt(h.rr);
   *flag = h.done;
+  return cudaGetLastError();
+}
+// x . Op x for Op = energy / mass / Laplace (FineOp): per-block partial sums, added up by the caller in block order
+cudaError_t launch_fine_quadratic_form(cudaStream_t st, int op, long long n_nodes, const double *d_coef, const double *x,
+                                       double *partial, int *n_partial) {
+  const int nb = (int)((n_nodes + kCgThreads - 1) / kCgThreads);
+  *n_partial = nb;
+  if (partial) k_fine_apply<<<nb, kCgThreads, 0, st>>>(op, n_nodes, d_coef, x, nullptr, nullptr, partial, nullptr);
   return cudaGetLastError();
 }
 

@@ -116,10 +116,24 @@ cudaError_t launch_coarse_rhs(cudaStream_t st, int n_patches, int s, const doubl
                               int nf_max);
 cudaError_t launch_prolongate(cudaStream_t st, long long n_fine, const double *phi, const double *u, double *u_fine,
                               int nf_max);
-size_t cg_workspace_doubles(int nrows);
-cudaError_t run_coarse_cg(cudaStream_t st, int nrows, const double *Kell, const double *b, double *x, double *work,
-                          int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
-                          long long *launches);
+// fine-grid operators of k_fine_apply (online.cuh)
+enum FineOp {
+  kFineStiffDirichlet = 0,  // coefficient-weighted stiffness, identity on the domain-boundary rows, boundary columns dropped
+  kFineEnergy = 1,          // the same without the boundary treatment: x.y = energy norm^2
+  kFineMass = 2,            // mass matrix: x.y = L2 norm^2
+  kFineLaplace = 3          // component-wise unweighted Laplace: x.y = H1 seminorm^2
+};
+struct CgOperator {
+  const double *Kell;     // block-ELL coarse matrix, or nullptr for the fine Dirichlet stiffness operator
+  const double *d_coef;   // fine operator: sub-cell coefficients
+  long long n_nodes;      // fine operator: nodes of the global grid
+};
+size_t cg_workspace_doubles(const CgOperator &A, int nrows);
+cudaError_t run_cg(cudaStream_t st, int nrows, const CgOperator &A, const double *b, double *x, double *work,
+                   int max_steps, double tol, double reduction, int *steps, double *residual, int *flag,
+                   long long *launches);
+cudaError_t launch_fine_quadratic_form(cudaStream_t st, int op, long long n_nodes, const double *d_coef, const double *x,
+                                       double *partial, int *n_partial);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);
 

@@ -145,8 +145,7 @@ k_cg_init(int nrows, const double *__restrict__ Kell, const double *__restrict__
   double rz = 0.0, rr = 0.0;
   for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
     const int d = i % s;
-    const double diag = Kell[(size_t)i * cP.ell_width + centre * s + d];
-    const double di = 1.0 / diag;
+    const double di = Kell ? 1.0 / Kell[(size_t)i * cP.ell_width + centre * s + d] : dinv[i];   // fine operator: preset
     const double ri = b[i];
     dinv[i] = di;
     x[i] = 0.0;
@@ -297,6 +296,110 @@ k_cg_direction(int nrows, int it, const double *__restrict__ r, const double *__
       if (rr <= tol2 || rr <= red2 * rr0) st->done = 1;
     }
   }
+}
+
+// ---- fine-scale operators on the global grid ----
+// Matrix-free Q_iso_Q1 operators on the (N n + 1)^dim node grid, one thread per node, y = Op x and per-block partial
+// sums of x.y.  The node's row is accumulated sub-cell by sub-cell from the same reference matrices the patch kernels
+// use (geom.h: Kref / Klam / Kq), so the fine FEM problem of assemble_and_solve_fem_problem (source/LOD.cc:1004-1094)
+// is exactly the operator the patch problems restrict.
+
+__device__ __forceinline__ double fine_local_entry(int op, const double *__restrict__ d_coef, long long sc, long long fstride,
+                                                   int la, int lb, int ca, int cb) {
+  const int dim = cP.dim, s = cP.s;
+  if (op == kFineMass || op == kFineLaplace) {
+    if (ca != cb) return 0.0;
+    double m[3] = {1.0, 1.0, 1.0};
+    int same[3] = {1, 1, 1};
+    for (int x = 0; x < dim; ++x) {
+      same[x] = (((la >> x) & 1) == ((lb >> x) & 1));
+      m[x] = same[x] ? cP.h / 3.0 : cP.h / 6.0;
+    }
+    if (op == kFineMass) return m[0] * m[1] * m[2];
+    double v = 0.0;
+    for (int k = 0; k < dim; ++k) {
+      double t = (same[k] ? 1.0 : -1.0) / cP.h;
+      for (int x = 0; x < dim; ++x) if (x != k) t *= m[x];
+      v += t;
+    }
+    return v;
+  }
+  const int nl = (1 << dim) * s;
+  const int idx = (la * s + ca) * nl + (lb * s + cb);
+  if (!cP.gauss_coef) {
+    if (cP.problem == 0) return d_coef[sc] * cP.Kref[idx];
+    return d_coef[fstride + sc] * cP.Kref[idx] + d_coef[sc] * cP.Klam[idx];
+  }
+  const int nq = 1 << dim;
+  double v = 0.0;
+  for (int q = 0; q < nq; ++q) {
+    if (cP.problem == 0) v += d_coef[sc * nq + q] * cP.Kq[q][idx];
+    else v += d_coef[(fstride + sc) * nq + q] * cP.Kq[q][idx] + d_coef[sc * nq + q] * cP.Klamq[q][idx];
+  }
+  return v;
+}
+
+// invdiag != nullptr: write 1 / diagonal of the operator instead of applying it (Jacobi preconditioner)
+__global__ void __launch_bounds__(kCgThreads)
+k_fine_apply(int op, long long n_nodes, const double *__restrict__ d_coef, const double *__restrict__ x,
+             double *__restrict__ y, double *__restrict__ invdiag, double *__restrict__ partial, const CgState *st) {
+  __shared__ double sRed[kCgThreads / 32];
+  if (st && st->done) return;
+  const int dim = cP.dim, s = cP.s, G = cP.nsub + 1, nsub = cP.nsub;
+  const long long fstride = (dim == 3) ? (long long)nsub * nsub * nsub : (long long)nsub * nsub;
+  const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dot = 0.0;
+  if (node < n_nodes) {
+    int a[3];
+    long long r = node;
+    a[0] = (int)(r % G);
+    r /= G;
+    a[1] = (dim >= 2) ? (int)(r % G) : 0;
+    a[2] = (dim == 3) ? (int)(r / G) : 0;
+    bool on_boundary = false;
+    for (int k = 0; k < dim; ++k) on_boundary = on_boundary || a[k] == 0 || a[k] == G - 1;
+    double acc[2] = {0.0, 0.0};
+    if (op == kFineStiffDirichlet && on_boundary) {
+      for (int c = 0; c < s; ++c) acc[c] = invdiag ? 1.0 : x[node * s + c];
+    } else {
+      for (int corner = 0; corner < (1 << dim); ++corner) {   // the sub-cell in which this node is local node `corner`
+        int o[3] = {0, 0, 0};
+        bool inside = true;
+        for (int k = 0; k < dim; ++k) {
+          o[k] = a[k] - ((corner >> k) & 1);
+          inside = inside && o[k] >= 0 && o[k] < nsub;
+        }
+        if (!inside) continue;
+        const long long sc = ((long long)o[2] * nsub + o[1]) * nsub + o[0];
+        for (int lb = 0; lb < (1 << dim); ++lb) {
+          int b[3] = {0, 0, 0};
+          bool b_boundary = false;
+          for (int k = 0; k < dim; ++k) {
+            b[k] = o[k] + ((lb >> k) & 1);
+            b_boundary = b_boundary || b[k] == 0 || b[k] == G - 1;
+          }
+          if (op == kFineStiffDirichlet && b_boundary) continue;
+          if (invdiag && lb != corner) continue;
+          const long long nb = ((long long)b[2] * G + b[1]) * G + b[0];
+          for (int ca = 0; ca < s; ++ca)
+            for (int cb = 0; cb < s; ++cb) {
+              if (invdiag && cb != ca) continue;
+              const double v = fine_local_entry(op, d_coef, sc, fstride, corner, lb, ca, cb);
+              acc[ca] += invdiag ? v : v * x[nb * s + cb];
+            }
+        }
+      }
+    }
+    for (int c = 0; c < s; ++c) {
+      if (invdiag) invdiag[node * s + c] = 1.0 / acc[c];
+      else {
+        if (y) y[node * s + c] = acc[c];
+        dot += acc[c] * x[node * s + c];
+      }
+    }
+  }
+  dot = block_sum(dot, sRed);
+  if (threadIdx.x == 0 && partial) partial[blockIdx.x] = dot;
 }
 
 }  // namespace slod

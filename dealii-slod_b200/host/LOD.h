@@ -12,8 +12,9 @@
 // builds per patch on the host (Triangulation, DoFHandler, sparsity patterns, index vectors) is closed-form index
 // arithmetic inside that library, so the host keeps only the parameter interface, the coefficient tables and the
 // results.  After the offline phase run() also does SURVEY.md section 8f row 1 through the same handle: fine right-hand
-// side (constant forcing), solve() = C^T f + coarse CG, and the prolongation C u.  The fine FEM reference solve, the
-// error tables and the VTU writers (section 8f rows 2-3) are out of scope and are not run.
+// side (constant forcing), solve() = C^T f + coarse CG, the prolongation C u and -- with "Compare with fine global
+// solution" -- section 8f row 2: the fine FEM reference solve and the SLOD-vs-FEM(h) error norms.  The other error
+// tables (exact solution, coarse FEM) and the VTU writers are out of scope and are not run.
 //
 // Error behaviour: like the reference (AssertThrow -> exception -> main prints and returns 1), every failing C ABI
 // call becomes a std::runtime_error carrying slod_last_error().
@@ -179,6 +180,9 @@ public:
     prm.declare(P + "/Solver/Coarse solver control", "Max steps", "100");
     prm.declare(P + "/Solver/Coarse solver control", "Tolerance", "1e-10");
     prm.declare(P + "/Solver/Coarse solver control", "Reduction", "1e-2");
+    prm.declare(P + "/Solver/Fine solver control", "Max steps", "100");      // include/LOD.h:108,126
+    prm.declare(P + "/Solver/Fine solver control", "Tolerance", "1e-10");
+    prm.declare(P + "/Solver/Fine solver control", "Reduction", "1e-2");
     prm.declare(P + "/B200", "Device", "-1");              // [+] CUDA device ordinal, -1 = current
     prm.declare(P + "/B200", "Write coarse matrix", "true");
   }
@@ -204,6 +208,9 @@ public:
     coarse_max_steps = (unsigned)nonneg(prm.get_integer(P + "/Solver/Coarse solver control", "Max steps"), "Max steps");
     coarse_tolerance = prm.get_double(P + "/Solver/Coarse solver control", "Tolerance");
     coarse_reduction = prm.get_double(P + "/Solver/Coarse solver control", "Reduction");
+    fine_max_steps = (unsigned)nonneg(prm.get_integer(P + "/Solver/Fine solver control", "Max steps"), "Max steps");
+    fine_tolerance = prm.get_double(P + "/Solver/Fine solver control", "Tolerance");
+    fine_reduction = prm.get_double(P + "/Solver/Fine solver control", "Reduction");
     device = (int)prm.get_integer(P + "/B200", "Device");
     write_coarse_matrix = prm.get_bool(P + "/B200", "Write coarse matrix");
     (void)rhs_constants();   // refuse what this host cannot evaluate before any work is done
@@ -224,6 +231,8 @@ public:
   std::string rhs_expression = spacedim == 1 ? "0" : "0; 0";
   unsigned int coarse_max_steps = 100;
   double coarse_tolerance = 1e-10, coarse_reduction = 1e-2;
+  unsigned int fine_max_steps = 100;
+  double fine_tolerance = 1e-10, fine_reduction = 1e-2;
   int device = -1;
   bool write_coarse_matrix = true;
 
@@ -372,11 +381,18 @@ public:
     create_random_problem_coefficients();
     compute_basis_function_candidates();
     assemble_global_matrix();
-    assemble_fem_rhs();
+    assemble_and_solve_fem_problem();
     solve();
-    prolongate_lod_solution();
-    // the fine FEM solve of assemble_and_solve_fem_problem, the error tables and the VTU writers are out of scope
+    compare_lod_with_fem();
+    // output_fine_results / output_coarse_results (VTU writers) are out of scope
     output_offline_results();
+    if (par.solve_fine_problem) {   // source/LOD.cc:1463-1465
+      pcout << "SLOD vs reference FEM(h)" << std::endl;
+      char buf[200];
+      std::snprintf(buf, sizeof buf, "cells dofs   u_L2_norm    u_H1_norm    u_energy_norm\n%5lld %6zu %12.6e %12.6e %12.6e",
+                    (long long)n_patches, n_dofs_fine, error_LOD_FEMh[0], error_LOD_FEMh[1], error_LOD_FEMh[2]);
+      pcout << buf << std::endl;
+    }
     computing_timer.print_summary(pcout);
   }
 
@@ -526,6 +542,37 @@ protected:
     pcout << "     fem rhs l2 norm = " << std::sqrt(nrm) << std::endl;   // source/LOD.cc:1039
   }
 
+  // source/LOD.cc:1004-1094: right-hand side always (solve() needs it), the fine solve only when
+  // "Compare with fine global solution" is set (source/LOD.cc:1043)
+  void assemble_and_solve_fem_problem() {
+    assemble_fem_rhs();
+    if (!par.solve_fine_problem) return;
+    TimerOutput::Scope t(computing_timer, "0: fine FEM solve (B200)");
+    fem_solution.assign(n_dofs_fine, 0.0);
+    int32_t steps = 0;
+    double residual = 0;
+    check(slod_fem_solve(slod, fem_rhs.data(), fem_solution.data(), (int32_t)par.fine_max_steps, par.fine_tolerance,
+                         par.fine_reduction, &steps, &residual),
+          "slod_fem_solve");
+    pcout << "   size of fem u " << fem_solution.size() << std::endl;   // source/LOD.cc:1092
+    char buf[128];
+    std::snprintf(buf, sizeof buf, "   fine CG: %d steps, residual %.3e", (int)steps, residual);
+    pcout << buf << std::endl;
+  }
+
+  void compare_lod_with_fem() {  // source/LOD.cc:1240-1260
+    prolongate_lod_solution();
+    if (!par.solve_fine_problem) return;
+    TimerOutput::Scope t(computing_timer, "5: compare FEM vs LOD (B200)");
+    std::vector<double> diff(n_dofs_fine);
+    for (size_t i = 0; i < n_dofs_fine; ++i) diff[i] = fem_solution[i] - lod_solution[i];
+    double l2 = 0, h1s = 0, en = 0;
+    check(slod_fine_norms(slod, diff.data(), &l2, &h1s, &en), "slod_fine_norms");
+    error_LOD_FEMh[0] = l2;
+    error_LOD_FEMh[1] = std::sqrt(l2 * l2 + h1s * h1s);   // deal.II's H1_norm is the full norm
+    error_LOD_FEMh[2] = en;
+  }
+
   void solve() {  // source/LOD.cc:975-1001
     TimerOutput::Scope t(computing_timer, "4: Solve LOD (B200)");
     system_rhs.assign(n_dofs_coarse, 0.0);
@@ -586,7 +633,9 @@ protected:
   size_t n_dofs_coarse = 0, n_dofs_fine = 0;
   std::vector<Patch<dim>> patches;
   CoarseMatrix global_stiffness_matrix;
-  std::vector<double> fem_rhs, system_rhs, solution, lod_solution;   // include/LOD.h:236-239, lexicographic fine numbering
+  // include/LOD.h:236-239, lexicographic fine numbering
+  std::vector<double> fem_rhs, fem_solution, system_rhs, solution, lod_solution;
+  double error_LOD_FEMh[3] = {0, 0, 0};   // L2, H1, energy norm of fem_solution - lod_solution (include/LOD.h:115)
 };
 
 // include/Diffusion.h:56-306.  The reference draws Alpha(1,100,8) in the constructor; here the table is drawn in

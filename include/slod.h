@@ -130,6 +130,19 @@ int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse,
 /* lod_solution = C u  (basis_matrix_transposed.vmult(lod_solution, solution), source/LOD.cc:1251). */
 int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine);
 
+/* ---- fine-scale reference problem (the solve of LOD::assemble_and_solve_fem_problem,
+ * source/LOD.cc:1004-1094, and the norms of compare_lod_with_fem, source/LOD.cc:1252).  Needs only the coefficient.
+ * A u = f on the global Q_iso_Q1 grid with homogeneous Dirichlet conditions (boundary rows of f are ignored, u = 0
+ * there), matrix free, by diag-preconditioned conjugate gradients (the reference: CG + AMG) with the same stopping
+ * rule and error behaviour as slod_coarse_solve. */
+int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t max_steps, double tolerance,
+                   double reduction, int32_t *steps, double *residual);
+/* Norms of a fine vector (outputs may be NULL): ||v||_L2 = sqrt(v.Mv) and |v|_H1 = sqrt(v.Lv) with the exact Q1 mass
+ * and Laplace matrices of the sub-cell grid, and the energy norm sqrt(v.Av) of the problem's own bilinear form.  The
+ * reference integrates |u_fem - u_lod| with a Gauss rule on the coarse cells (ParsedConvergenceTable::difference),
+ * which is not exact for Q_iso_Q1 functions; these are the exact values of the same norms. */
+int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_semi, double *energy);
+
 /* Page-locked host memory for the caller-owned output buffers of slod_get_all_basis / slod_get_coarse_csr: copies
  * into pageable memory work too but run at a fraction of the link speed.  No reference counterpart. */
 int slod_alloc_host(size_t bytes, void **out);

@@ -697,6 +697,29 @@ class SlodOracle:
         u[ii] = spla.spsolve(A[ii][:, ii].tocsc(), np.asarray(F, dtype=float)[ii])
         return u, A
 
+    def fine_norm_matrices(self):
+        """Exact Q1 mass matrix and component-wise Laplace matrix of the sub-cell grid: ||v||_L2^2 = v.Mv and
+        |v|_H1^2 = v.Lv are the norms compare_lod_with_fem tabulates (source/LOD.cc:1252; the reference integrates them
+        with a Gauss rule on the coarse cells, which is not exact for Q_iso_Q1 functions).  Lexicographic numbering."""
+        pr = self.prob
+        dim, s, h = pr.dim, pr.spacedim, pr.h
+        G = pr.N * pr.n_subdivisions + 1
+        m1 = sp.diags([np.full(G - 1, h / 6), np.r_[h / 3, np.full(G - 2, 2 * h / 3), h / 3], np.full(G - 1, h / 6)],
+                      [-1, 0, 1])
+        k1 = sp.diags([np.full(G - 1, -1 / h), np.r_[1 / h, np.full(G - 2, 2 / h), 1 / h], np.full(G - 1, -1 / h)],
+                      [-1, 0, 1])
+
+        def kron_chain(mats):           # x fastest: the x factor is the innermost (last) Kronecker factor
+            out = mats[-1]
+            for m in reversed(mats[:-1]):
+                out = sp.kron(out, m)
+            return out
+
+        M = kron_chain([m1] * dim)
+        L = sum(kron_chain([k1 if a == k else m1 for a in range(dim)]) for k in range(dim))
+        eye = sp.identity(s)
+        return sp.kron(M, eye).tocsr(), sp.kron(L, eye).tocsr()
+
     # -- LOD::solve (source/LOD.cc:975-1001) and the prolongation (source/LOD.cc:1251) -----------------------------
     @staticmethod
     def solve_coarse(K, b, max_steps=100, tolerance=1e-10, reduction=1e-10, omega=1.2, direct=False):

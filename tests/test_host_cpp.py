@@ -16,6 +16,7 @@ PRM = """subsection Problem
   set Number of subdivisions = 2
   set Number of global refinements = {ref}
   set Stabilize phi_LOD candidates = true   # SLOD
+  set Compare with fine global solution = true
   subsection Coefficients
     set Constant problem coefficients = false
     set Refinement for random coefficients = {r}
@@ -27,6 +28,11 @@ PRM = """subsection Problem
   subsection Solver
     subsection Coarse solver control
       set Max steps = 2000
+      set Tolerance = 0
+      set Reduction = 1e-12
+    end
+    subsection Fine solver control
+      set Max steps = 100000
       set Tolerance = 0
       set Reduction = 1e-12
     end
@@ -129,3 +135,13 @@ def test_apps_match_oracle(apps, tmp_path, app, dim, s, ref, ell, r):
     u, _ = orc.solve_coarse(K, b, direct=True)
     nrm = float(re.search(r"lod solution l2 norm = (\S+)", out).group(1))
     assert abs(nrm - np.linalg.norm(C @ u)) <= 1e-7 * np.linalg.norm(C @ u)
+    # compare_lod_with_fem (source/LOD.cc:1240-1260): the SLOD vs FEM(h) table
+    assert f"size of fem u {s * (2 ** ref * 2 + 1) ** dim}" in out
+    u_fem, A = orc.fem_solve(f)
+    M, L = orc.fine_norm_matrices()
+    e = u_fem - C @ u
+    row = out.split("SLOD vs reference FEM(h)")[1].split("\n")[2].split()
+    l2, h1, en = float(row[2]), float(row[3]), float(row[4])
+    assert abs(l2 - np.sqrt(e @ (M @ e))) <= 1e-4 * l2
+    assert abs(h1 - np.sqrt(e @ (M @ e) + e @ (L @ e))) <= 1e-4 * h1
+    assert abs(en - np.sqrt(e @ (A @ e))) <= 1e-4 * en
