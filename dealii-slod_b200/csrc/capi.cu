@@ -82,6 +82,8 @@ struct slod_ctx {
   bool csr_ready = false;
   std::vector<int64_t> csr_rowptr, csr_col;
   long long *d_perm = nullptr;   // CSR entry -> position in the block-ELL array
+  double *d_online = nullptr;    // scratch of the online / fine-problem entry points, allocated on first use
+  size_t online_doubles = 0;
   double *d_val = nullptr;
   int64_t csr_nnz = 0;
 };
@@ -247,7 +249,7 @@ void free_dev(slod_ctx *c) {
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
   F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
-  F(c->d_perm); F(c->d_val);
+  F(c->d_perm); F(c->d_val); F(c->d_online);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
 }
 
@@ -1083,6 +1085,32 @@ int slod_get_coarse_csr(const slod_ctx *cctx, int64_t *rowptr, int64_t *col, dou
 }
 
 // ---- online phase on the handle's own basis and coarse matrix ----
+// One scratch block for all of these entry points (cudaMalloc / cudaFree per call costs milliseconds next to the tens
+// of GB the handle has mapped): [2 fine vectors | 2 coarse vectors | CG workspace of the larger problem].
+static int online_scratch(slod_ctx *ctx, double **fine_a, double **fine_b, double **coarse_a, double **coarse_b,
+                          double **work) {
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
+  const CgOperator Ac{reinterpret_cast<const double *>(1), nullptr, 0}, Af{nullptr, nullptr, n_fine / ctx->P.s};
+  const size_t wk = std::max(cg_workspace_doubles(Ac, (int)nc), cg_workspace_doubles(Af, (int)n_fine));
+  const size_t need = 2 * (size_t)n_fine + 2 * nc + wk + 8;
+  if (ctx->online_doubles < need) {
+    if (ctx->d_online) cudaFree(ctx->d_online);
+    ctx->d_online = nullptr;
+    ctx->online_doubles = 0;
+    CK(cudaMalloc(&ctx->d_online, sizeof(double) * need));
+    ctx->online_doubles = need;
+  }
+  double *p = ctx->d_online;
+  if (fine_a) *fine_a = p;
+  if (fine_b) *fine_b = p + n_fine;
+  if (coarse_a) *coarse_a = p + 2 * n_fine;
+  if (coarse_b) *coarse_b = p + 2 * n_fine + nc;
+  if (work) *work = p + 2 * n_fine + 2 * nc;
+  return SLOD_OK;
+}
+
 int slod_fine_size(const slod_ctx *ctx, int64_t *n_fine) {
   if (!ctx || !n_fine) return SLOD_ERR_INVALID;
   int64_t n = ctx->P.s;
@@ -1102,14 +1130,12 @@ int slod_coarse_rhs(slod_ctx *ctx, const double *f_fine, double *rhs_coarse) {
   slod_fine_size(ctx, &n_fine);
   const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
   double *d_f = nullptr, *d_b = nullptr;
-  CK(cudaMalloc(&d_f, sizeof(double) * (size_t)n_fine));
-  cudaError_t e = cudaMalloc(&d_b, sizeof(double) * nc);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, f_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
+  int rc = online_scratch(ctx, &d_f, nullptr, &d_b, nullptr, nullptr);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpyAsync(d_f, f_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
   if (e == cudaSuccess) e = launch_coarse_rhs(0, (int)ctx->n_patches, ctx->P.s, ctx->d_phi, d_f, d_b, ctx->P.NfMax);
   if (e == cudaSuccess) e = cudaMemcpyAsync(rhs_coarse, d_b, sizeof(double) * nc, cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_f);
-  cudaFree(d_b);
   ctx->launches += 1;
   if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_coarse_rhs: ") + cudaGetErrorString(e));
   return SLOD_OK;
@@ -1127,10 +1153,10 @@ int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse,
   CK(upload_params(ctx->P));
   const int nrows = (int)(ctx->n_patches * ctx->P.s);
   double *d_b = nullptr, *d_x = nullptr, *d_work = nullptr;
-  CK(cudaMalloc(&d_b, sizeof(double) * 2 * (size_t)nrows));
-  d_x = d_b + nrows;
+  int rc = online_scratch(ctx, nullptr, nullptr, &d_b, &d_x, &d_work);
+  if (rc) return rc;
   const CgOperator A{ctx->d_Kell, nullptr, 0};
-  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(A, nrows));
+  cudaError_t e = cudaSuccess;
   int st_steps = 0, flag = 0;
   long long n_launch = 0;
   double res = 0.0;
@@ -1140,8 +1166,6 @@ int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse,
                       &n_launch);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u_coarse, d_x, sizeof(double) * nrows, cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_b);
-  cudaFree(d_work);
   ctx->launches += n_launch;
   if (steps) *steps = st_steps;
   if (residual) *residual = res;
@@ -1166,14 +1190,13 @@ int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine) {
   slod_fine_size(ctx, &n_fine);
   const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
   double *d_u = nullptr, *d_f = nullptr;
-  CK(cudaMalloc(&d_u, sizeof(double) * nc));
-  cudaError_t e = cudaMalloc(&d_f, sizeof(double) * (size_t)n_fine);
+  int rc = online_scratch(ctx, &d_f, nullptr, &d_u, nullptr, nullptr);
+  if (rc) return rc;
+  cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, u_coarse, sizeof(double) * nc, cudaMemcpyHostToDevice, 0);
   if (e == cudaSuccess) e = launch_prolongate(0, n_fine, ctx->d_phi, d_u, d_f, ctx->P.NfMax);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u_fine, d_f, sizeof(double) * (size_t)n_fine, cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_u);
-  cudaFree(d_f);
   ctx->launches += 1;
   if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_prolongate: ") + cudaGetErrorString(e));
   return SLOD_OK;
@@ -1210,10 +1233,10 @@ int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t 
       for (int c = 0; c < P.s; ++c) f[node * P.s + c] = 0.0;
   }
   const CgOperator A{nullptr, ctx->d_coef, n_nodes};
-  double *d_b = nullptr, *d_work = nullptr;
-  CK(cudaMalloc(&d_b, sizeof(double) * 2 * (size_t)n_fine));
-  double *d_x = d_b + n_fine;
-  cudaError_t e = cudaMalloc(&d_work, sizeof(double) * cg_workspace_doubles(A, (int)n_fine));
+  double *d_b = nullptr, *d_x = nullptr, *d_work = nullptr;
+  rc = online_scratch(ctx, &d_b, &d_x, nullptr, nullptr, &d_work);
+  if (rc) return rc;
+  cudaError_t e = cudaSuccess;
   int st_steps = 0, flag = 0;
   long long n_launch = 0;
   double res = 0.0;
@@ -1222,8 +1245,6 @@ int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t 
     e = run_cg(0, (int)n_fine, A, d_b, d_x, d_work, max_steps, tolerance, reduction, &st_steps, &res, &flag, &n_launch);
   if (e == cudaSuccess) e = cudaMemcpyAsync(u_fine, d_x, sizeof(double) * (size_t)n_fine, cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_b);
-  cudaFree(d_work);
   ctx->launches += n_launch;
   if (steps) *steps = st_steps;
   if (residual) *residual = res;
@@ -1250,9 +1271,10 @@ int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_
   const long long n_nodes = n_fine / ctx->P.s;
   int nb = 0;
   launch_fine_quadratic_form(0, kFineMass, n_nodes, nullptr, nullptr, nullptr, &nb);
-  double *d_v = nullptr, *d_part = nullptr;
-  CK(cudaMalloc(&d_v, sizeof(double) * (size_t)n_fine));
-  cudaError_t e = cudaMalloc(&d_part, sizeof(double) * 3 * (size_t)nb);
+  double *d_v = nullptr, *d_part = nullptr;   // 3 nb <= n_fine: the partial sums fit the second fine vector
+  rc = online_scratch(ctx, &d_v, &d_part, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  cudaError_t e = cudaSuccess;
   std::vector<double> part(3 * (size_t)nb);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, v_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
   const int ops[3] = {kFineMass, kFineLaplace, kFineEnergy};
@@ -1261,8 +1283,6 @@ int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_v);
-  cudaFree(d_part);
   ctx->launches += 3;
   if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_fine_norms: ") + cudaGetErrorString(e));
   double sum[3] = {0, 0, 0};
