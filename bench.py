@@ -355,7 +355,7 @@ def main():
         for _ in range(w["dim"] - 1):
             f = np.multiply.outer(w1, f)
         f = np.repeat(f.ravel(), s)
-        ctx.prolongate(ctx.coarse_solve(ctx.coarse_rhs(f), max_steps=2, tolerance=0.0, reduction=0.5)[0])   # first-launch costs
+        ctx.prolongate(ctx.coarse_solve(ctx.coarse_rhs(f), max_steps=5, tolerance=0.0, reduction=1e9)[0])   # first-launch costs (one CG step)
         t0 = time.perf_counter()
         b = ctx.coarse_rhs(f)
         t1 = time.perf_counter()
