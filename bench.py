@@ -303,14 +303,14 @@ def main():
                 for f, tb in enumerate(tables):
                     ctx.set_coefficient(f, w["r"], tb)
                 ctx.compute_basis()
-                ctx.assemble_coarse()
-                rowptr, col, val = ctx.coarse_csr()
+                ctx.assemble_coarse()            # enqueues; the basis read-back below overlaps the coarse kernels
                 ph, aph = ctx.all_basis()
+                rowptr, col, val = ctx.coarse_csr()
                 e2e_bytes[0] = val.nbytes + ph.nbytes + aph.nbytes
                 return float(val[0] + ph[0, 0, 0])
             e2e_bytes = [0]
             d2h = None
-            path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_coarse_csr+slod_get_all_basis"
+            path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_all_basis+slod_get_coarse_csr"
         else:
             h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
             h_aphi = torch.empty_like(h_phi, pin_memory=True)

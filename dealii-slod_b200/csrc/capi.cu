@@ -82,6 +82,8 @@ struct slod_ctx {
   bool csr_ready = false;
   std::vector<int64_t> csr_rowptr, csr_col;
   long long *d_perm = nullptr;   // CSR entry -> position in the block-ELL array
+  cudaStream_t copy_stream = nullptr;   // non-blocking: result read-back overlaps the coarse-matrix kernels
+  bool coarse_timing_pending = false;
   double *d_online = nullptr;    // scratch of the online / fine-problem entry points, allocated on first use
   size_t online_doubles = 0;
   double *d_val = nullptr;
@@ -422,8 +424,18 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
   return SLOD_OK;
 }
 
+int finish_coarse_timing(slod_ctx *ctx) {
+  if (!ctx->coarse_timing_pending) return SLOD_OK;
+  ctx->coarse_timing_pending = false;
+  CK(cudaEventSynchronize(ctx->ev[6]));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
+  ctx->tm.ms[4] = ms;
+  return SLOD_OK;
+}
+
 int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const double *d_aphi, double *d_K,
-               cudaStream_t st) {
+               cudaStream_t st, bool wait = true) {
   if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
   if (p0 == p1) return SLOD_OK;
   CK(upload_params(ctx->P));
@@ -436,11 +448,9 @@ int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const
                      d_aphi, d_K, ctx->fl));
   CK(cudaEventRecord(ctx->ev[6], st));
   ctx->launches += 1;
-  CK(cudaEventSynchronize(ctx->ev[6]));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
-  ctx->tm.ms[4] = ms;
-  return SLOD_OK;
+  ctx->coarse_timing_pending = true;
+  if (!wait) return SLOD_OK;
+  return finish_coarse_timing(ctx);
 }
 
 // block-ELL -> CSR.  The pattern is integer geometry: (p, q) is structural iff the node boxes intersect.
@@ -785,6 +795,8 @@ void slod_destroy(slod_ctx *ctx) {
     return;
   }
   cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();   // slod_assemble_coarse only enqueues
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   free_dev(ctx);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1001,8 +1013,13 @@ int slod_get_all_basis(const slod_ctx *ctx, double *phi, double *aphi) {
   if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
   const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax;
   CK(cudaSetDevice(ctx->device));
-  if (phi) CK(cudaMemcpy(phi, ctx->d_phi, sizeof(double) * n, cudaMemcpyDeviceToHost));
-  if (aphi) CK(cudaMemcpy(aphi, ctx->d_aphi, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  // slod_compute_basis returned synchronised, so the basis is complete; the copies go through a non-blocking stream and
+  // overlap whatever slod_assemble_coarse has in flight
+  slod_ctx *c = const_cast<slod_ctx *>(ctx);
+  if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (phi) CK(cudaMemcpyAsync(phi, ctx->d_phi, sizeof(double) * n, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (aphi) CK(cudaMemcpyAsync(aphi, ctx->d_aphi, sizeof(double) * n, cudaMemcpyDeviceToHost, c->copy_stream));
+  CK(cudaStreamSynchronize(c->copy_stream));
   return SLOD_OK;
 }
 
@@ -1048,13 +1065,14 @@ int slod_assemble_coarse(slod_ctx *ctx) {
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.ell_width;
   if (!ctx->d_Kell) CK(cudaMalloc(&ctx->d_Kell, sizeof(double) * n));
-  int rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0);
+  // The kernels are only enqueued: slod_get_all_basis (own copy stream) can run while they execute, every consumer of
+  // the matrix is stream ordered behind them, and an execution error surfaces at that consumer's synchronisation.
+  int rc = build_csr_cache(ctx);   // first call only: host-side integer geometry, before the kernels are in flight
   if (rc) return rc;
-  rc = build_csr_cache(ctx);
+  rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0, false);
   if (rc) return rc;
   CK(launch_gather(0, ctx->d_Kell, ctx->d_perm, ctx->d_val, ctx->csr_nnz));   // compact block-ELL -> CSR values
   ctx->launches += 1;
-  CK(cudaDeviceSynchronize());
   ctx->coarse_done = true;
   return SLOD_OK;
 }
@@ -1365,6 +1383,10 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
 
 int slod_get_timings(const slod_ctx *ctx, double *ms, int n) {
   if (!ctx || !ms) return SLOD_ERR_INVALID;
+  if (ctx->coarse_timing_pending && ctx->device != SLOD_DEVICE_NONE) {
+    int rc = finish_coarse_timing(const_cast<slod_ctx *>(ctx));
+    if (rc) return rc;
+  }
   for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->tm.ms[i];
   return SLOD_OK;
 }

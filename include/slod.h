@@ -106,7 +106,9 @@ int slod_get_basis(const slod_ctx *ctx, int64_t patch, int comp, double *phi, do
 /* all patches at once: arrays [n_patches][spacedim][stride] with stride = slod_basis_stride(). */
 int slod_basis_stride(const slod_ctx *ctx, int64_t *stride);
 int slod_get_all_basis(const slod_ctx *ctx, double *phi, double *A_phi);
-/* global_stiffness_matrix = C^T (A C)  (source/LOD.cc:860-973). */
+/* global_stiffness_matrix = C^T (A C)  (source/LOD.cc:860-973).  The kernels are enqueued and the call returns: every
+ * consumer of the matrix (slod_get_coarse_csr, slod_coarse_solve, ...) is ordered behind them and reports an execution
+ * error at its own synchronisation, and slod_get_all_basis, called in between, copies while they run. */
 int slod_assemble_coarse(slod_ctx *ctx);
 /* CSR of the coarse matrix (rows/cols = spacedim*patch + comp, columns ascending; structural zeros of
  * the sparse product are kept).  Call with rowptr == NULL to query n_rows and nnz. */
