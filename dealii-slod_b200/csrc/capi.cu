@@ -47,6 +47,7 @@ struct slod_ctx {
   double *d_phi = nullptr, *d_aphi = nullptr, *d_Kell = nullptr, *d_diag = nullptr;
   int *d_status = nullptr;
   int *d_counter = nullptr;
+  int *d_work_counter = nullptr;   // next work item of the persistent solver / flux / dense kernels
   bool basis_done = false, coarse_done = false;
   // chunk workspaces
   int chunk = 0;
@@ -250,7 +251,7 @@ void free_dev(slod_ctx *c) {
     p = nullptr;
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
-  F(c->d_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
+  F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
   F(c->d_perm); F(c->d_val); F(c->d_online);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
 }
@@ -320,6 +321,7 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   ctx->chunk = (int)chunk;
   CK(cudaMalloc(&ctx->d_ids, sizeof(int) * chunk));
   CK(cudaMalloc(&ctx->d_counter, sizeof(int) * 4));
+  CK(cudaMalloc(&ctx->d_work_counter, sizeof(int) * 4));
   CK(cudaMalloc(&ctx->d_X, sizeof(double) * (size_t)ctx->sl.x_stride * chunk));
   CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
   CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
@@ -379,6 +381,8 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
   }
   const std::vector<int> &ids = ctx->ids;
 
+  static const bool static_stride = getenv("SLOD_STATIC_WORK") != nullptr;   // A/B switch of the work distribution
+  int *wc = static_stride ? nullptr : ctx->d_work_counter;
   float acc[4] = {0, 0, 0, 0};
   for (size_t off = 0; off < ids.size(); off += ctx->chunk) {
     const int nw = (int)std::min<size_t>(ctx->chunk, ids.size() - off);
@@ -387,17 +391,17 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     if (ctx->mma_variant >= 0)
       CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx,
-                                ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw));
+                                ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw, wc));
     else
       CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Lws, ctx->d_status, ctx->sl));
     CK(cudaEventRecord(ctx->ev[1], st));
     if (ctx->dense_ntile) {
       CK(launch_patch_flux(std::min(nw, ctx->grid_flux), ctx->smem_flux, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
-                           ctx->d_W, ctx->xl));
+                           ctx->d_W, ctx->xl, wc));
       CK(launch_patch_dense_mma(ctx->dense_ntile, std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_W, ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status,
-                                ctx->dl));
+                                ctx->dl, wc));
       ctx->launches += 1;
     }
     else

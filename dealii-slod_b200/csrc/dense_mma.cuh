@@ -19,7 +19,8 @@ template <int NTILE>
 __global__ void __launch_bounds__(32 * NTILE, 1)
 k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
                   const double *__restrict__ Xbuf, const double *__restrict__ Wbuf, double *__restrict__ Minv_out,
-                  double *__restrict__ G_out, double *__restrict__ diag, int *__restrict__ status, DenseLayout lay) {
+                  double *__restrict__ G_out, double *__restrict__ diag, int *__restrict__ status, DenseLayout lay,
+                  int *work_counter) {
   constexpr int NT = 32 * NTILE;
   constexpr int NC = 8 * NTILE;   // padded coarse dimension
   constexpr int LDM = NC + 4;     // LDM % 16 == 4 : conflict-free fragment loads
@@ -39,7 +40,9 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   // have fewer interior nodes under them, consecutive rows would leave some warps with much less to gather)
   constexpr int RSTR = 2 * NTILE;
 
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  __shared__ int sNextWork;
+  SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
+    fetch_work_item(w, work_counter, &sNextWork);
     const int pid = patch_ids[w];
     const Geom geo = make_geom(cP, pid);
     const int ncd = geo.Ncd, s = cP.s;

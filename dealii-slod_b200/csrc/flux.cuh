@@ -16,7 +16,7 @@ constexpr int kFNB = 56;    // stencil slots reserved per boundary row (27 * spa
 
 __global__ void __launch_bounds__(256, 4)
 k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
-             const double *__restrict__ Xbuf, double *__restrict__ Wbuf, FluxLayout lay) {
+             const double *__restrict__ Xbuf, double *__restrict__ Wbuf, FluxLayout lay, int *work_counter) {
   extern __shared__ double smem[];
   const int NC = lay.ldx, LDT = NC + 4;
   double *sCoef = smem;
@@ -28,7 +28,9 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
   __shared__ int sNb;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NWARP = NT >> 5;
 
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  __shared__ int sNextWork;
+  SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
+    fetch_work_item(w, work_counter, &sNextWork);
     const Geom geo = make_geom(cP, patch_ids[w]);
     if (!geo.slod) continue;
     const int ncd = geo.Ncd, s = cP.s;

@@ -288,6 +288,23 @@ k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__res
 }
 
 }  // namespace slod
+// Persistent kernels fetch their next work item from a global counter (zeroed before the launch) instead of striding by
+// the grid size: items are sorted by cost, largest first, and a CTA that starts late -- because another stream's CTAs
+// hold its SM -- takes less work instead of finishing late.  The fetch is issued at the top of an item by the last
+// thread (its result is only needed at the end of the item); work_counter == nullptr keeps the static stride.
+#define SLOD_WORK_LOOP(w, n_work, work_counter, sNext)                                                        \
+  for (int w = blockIdx.x; w < (n_work); w = next_work_item(&(sNext)))
+__device__ __forceinline__ int next_work_item(int *sNext) {
+  __syncthreads();
+  const int v = *sNext;
+  __syncthreads();   // everybody has read it before the next item's fetch overwrites it
+  return v;
+}
+__device__ __forceinline__ void fetch_work_item(int w, int *work_counter, int *sNext) {
+  if (threadIdx.x == blockDim.x - 1)
+    *sNext = work_counter ? (int)gridDim.x + atomicAdd(work_counter, 1) : w + (int)gridDim.x;
+}
+
 #include "solve_mma.cuh"
 namespace slod {
 
@@ -867,10 +884,10 @@ cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int
 }
 template <int RBMAX, int NW>
 static cudaError_t launch_mma_t(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                                double *X, double *Lws, int *status, const SolveMmaLayout &lay) {
+                                double *X, double *Lws, int *status, const SolveMmaLayout &lay, int *work_counter) {
   cudaError_t e = cudaFuncSetAttribute(k_patch_solve_mma<RBMAX, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_patch_solve_mma<RBMAX, NW><<<grid, 32 * NW, smem, st>>>(ids, n_work, coef, X, Lws, status, lay);
+  k_patch_solve_mma<RBMAX, NW><<<grid, 32 * NW, smem, st>>>(ids, n_work, coef, X, Lws, status, lay, work_counter);
   return cudaGetLastError();
 }
 size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw) {
@@ -883,12 +900,16 @@ size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw) {
 }
 cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
-                                   long long x_stride, long long lws_per_cta, int nip_max, int stw) {
+                                   long long x_stride, long long lws_per_cta, int nip_max, int stw, int *work_counter) {
   SolveMmaLayout lay{coef_doubles, nip_max, stw, ldx, x_stride, lws_per_cta};
+  if (work_counter) {
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
   switch (variant) {
-    case 0: return launch_mma_t<13, 16>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
-    case 1: return launch_mma_t<4, 4>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
-    case 2: return launch_mma_t<4, 8>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay);
+    case 0: return launch_mma_t<13, 16>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay, work_counter);
+    case 1: return launch_mma_t<4, 4>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay, work_counter);
+    case 2: return launch_mma_t<4, 8>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay, work_counter);
   }
   return cudaErrorInvalidValue;
 }
@@ -904,10 +925,10 @@ cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int
 template <int NTILE>
 static cudaError_t launch_dense_t(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                   const double *X, const double *W, double *Minv, double *G, double *diag, int *status,
-                                  const DenseLayout &lay) {
+                                  const DenseLayout &lay, int *work_counter) {
   cudaError_t e = cudaFuncSetAttribute(k_patch_dense_mma<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_patch_dense_mma<NTILE><<<grid, 32 * NTILE, smem, st>>>(ids, n_work, coef, X, W, Minv, G, diag, status, lay);
+  k_patch_dense_mma<NTILE><<<grid, 32 * NTILE, smem, st>>>(ids, n_work, coef, X, W, Minv, G, diag, status, lay, work_counter);
   return cudaGetLastError();
 }
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
@@ -918,11 +939,15 @@ size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
 }
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, const double *W, double *Minv, double *G,
-                                   double *diag, int *status, const DenseLayout &lay) {
+                                   double *diag, int *status, const DenseLayout &lay, int *work_counter) {
+  if (work_counter) {
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+  }
   switch (ntile) {
-    case 4: return launch_dense_t<4>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
-    case 8: return launch_dense_t<8>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
-    case 16: return launch_dense_t<16>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay);
+    case 4: return launch_dense_t<4>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay, work_counter);
+    case 8: return launch_dense_t<8>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay, work_counter);
+    case 16: return launch_dense_t<16>(grid, smem, st, ids, n_work, coef, X, W, Minv, G, diag, status, lay, work_counter);
   }
   return cudaErrorInvalidValue;
 }
@@ -931,10 +956,11 @@ size_t flux_smem(int coef_doubles, int ldx, int nb_max) {
          sizeof(int) * ((size_t)kFTB * kFNB + kFTB + nb_max + 8);
 }
 cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                              const double *X, double *W, const FluxLayout &lay) {
+                              const double *X, double *W, const FluxLayout &lay, int *work_counter) {
   cudaError_t e = cudaFuncSetAttribute(k_patch_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_patch_flux<<<grid, 256, smem, st>>>(ids, n_work, coef, X, W, lay);
+  if (work_counter && (e = cudaMemsetAsync(work_counter, 0, sizeof(int), st)) != cudaSuccess) return e;
+  k_patch_flux<<<grid, 256, smem, st>>>(ids, n_work, coef, X, W, lay, work_counter);
   return cudaGetLastError();
 }
 

@@ -57,19 +57,20 @@ cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int
 size_t solve_mma_smem(int variant, int coef_doubles, int nip_max, int stw);
 cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
-                                   long long x_stride, long long lws_per_cta, int nip_max, int stw);
+                                   long long x_stride, long long lws_per_cta, int nip_max, int stw,
+                                   int *work_counter = nullptr);
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);
 // boundary flux W = S_b X - P_b for the tensor-core dense stage
 size_t flux_smem(int coef_doubles, int ldx, int nb_max);
 cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                              const double *X, double *W, const FluxLayout &lay);
+                              const double *X, double *W, const FluxLayout &lay, int *work_counter = nullptr);
 // tensor-core dense stage, ntile in {4, 8, 16} (8*ntile >= coarse dofs per patch)
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max);
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, const double *W, double *Minv, double *G,
-                                   double *diag, int *status, const DenseLayout &lay);
+                                   double *diag, int *status, const DenseLayout &lay, int *work_counter = nullptr);
 // selection pipeline (select.cuh): fast path -> tridiagonalisation + QL (rotation log) -> Jacobi fallback
 struct EigLayout {
   int nmax, ldh;

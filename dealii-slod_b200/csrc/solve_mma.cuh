@@ -100,7 +100,8 @@ __device__ __forceinline__ void lower_offset(int e, int dl[3]) {
 template <int RBMAX, int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
-                  double *__restrict__ Xbuf, double *__restrict__ Lws, int *__restrict__ status, SolveMmaLayout lay) {
+                  double *__restrict__ Xbuf, double *__restrict__ Lws, int *__restrict__ status, SolveMmaLayout lay,
+                  int *work_counter) {
   constexpr int R = 8 * RBMAX;
   constexpr int LDWF = (R % 16 == 8) ? R : R + 8;  // row stride with LDWF % 16 == 8 : conflict-free C fragments
   constexpr int LDP = R + 4;                        // k-major panel copy, LDP % 16 in {4, 12}
@@ -130,7 +131,9 @@ k_patch_solve_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     sTileTab[tt] = offI | ((tt - offI * (offI - 1) / 2 + 1) << 8);
   }
 
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  __shared__ int sNextWork;
+  SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
+    fetch_work_item(w, work_counter, &sNextWork);
     const int pid = patch_ids[w];
     const Geom geo = make_geom(cP, pid);
     const int Ni = geo.Ni, bw = geo.bw, ncd = geo.Ncd;
