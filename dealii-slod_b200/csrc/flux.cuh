@@ -12,16 +12,15 @@
 namespace slod {
 
 constexpr int kFTB = 32;    // boundary rows per pass
-constexpr int kFNB = 56;    // stencil slots reserved per boundary row (27 * spacedim <= 54)
+constexpr int kFNB = 20;    // stencil slots per boundary row: only inward offsets couple, 3^(dim-1) * spacedim <= 18
 
 __global__ void __launch_bounds__(256, 4)
 k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
              const double *__restrict__ Xbuf, double *__restrict__ Wbuf, FluxLayout lay, int *work_counter) {
   extern __shared__ double smem[];
-  const int NC = lay.ldx, LDT = NC + 4;
+  const int NC = lay.ldx;
   double *sCoef = smem;
-  double *sT = sCoef + lay.coef_doubles;        // [kFTB][LDT]
-  double *sArow = sT + kFTB * LDT;              // [kFTB][kFNB]
+  double *sArow = sCoef + lay.coef_doubles;     // [kFTB][kFNB]
   int *sAnbr = (int *)(sArow + kFTB * kFNB);    // [kFTB][kFNB]
   int *sAcnt = sAnbr + kFTB * kFNB;             // [kFTB]
   int *sBlist = sAcnt + kFTB;                   // [nb_max]
@@ -137,15 +136,18 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
               acc[u].y += av * xv.y;
             }
           }
+          // straight to W: a warp covers 512 contiguous bytes of a row; rows past the last dof of the pass and the
+          // padding columns carry zeros (empty stencil lists / cmax = 0)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int rb = r0 + u * rows_per_pass;
-            if (rb < kFTB) *reinterpret_cast<double2 *>(sT + rb * LDT + 2 * c2) = acc[u];
+            if (rb < kFTB) *reinterpret_cast<double2 *>(W + (size_t)(t0 + rb) * lay.ldx + 2 * c2) = acc[u];
           }
         }
       }
-      __syncthreads();
-      // ... - P_b : every boundary dof lies in at most 2^dim coarse cells
+      __syncthreads();   // the rows are visible to the whole CTA; the stencil lists may be rebuilt
+      // ... - P_b : every boundary dof lies in at most 2^dim coarse cells, each in its own column: a read-modify-write
+      // of the row just written (L2), not waited for -- the next pass touches other rows
       for (int idx = tid; idx < nt * 8; idx += NT) {
         const int rb = idx >> 3, corner = idx & 7;
         if (corner >= (1 << cP.dim)) continue;
@@ -166,16 +168,8 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
             if (rem != 0) wgt *= 2.0;
           }
         }
-        if (ok) sT[rb * LDT + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
+        if (ok) W[(size_t)(t0 + rb) * lay.ldx + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
       }
-      __syncthreads();
-      // write the pass (zero padded rows included): 16-byte stores, coalesced
-      for (int idx = tid; idx < kFTB * (NC / 2); idx += NT) {
-        const int rb = idx / (NC / 2), c2 = idx - rb * (NC / 2);
-        *reinterpret_cast<double2 *>(W + (size_t)(t0 + rb) * lay.ldx + 2 * c2) =
-            *reinterpret_cast<const double2 *>(sT + rb * LDT + 2 * c2);
-      }
-      __syncthreads();
     }
   }
 }

@@ -952,7 +952,8 @@ cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_
   return cudaErrorInvalidValue;
 }
 size_t flux_smem(int coef_doubles, int ldx, int nb_max) {
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)kFTB * (ldx + 4) + (size_t)kFTB * kFNB) +
+  (void)ldx;
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)kFTB * kFNB) +
          sizeof(int) * ((size_t)kFTB * kFNB + kFTB + nb_max + 8);
 }
 cudaError_t launch_patch_flux(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
