@@ -11,7 +11,7 @@
 
 namespace slod {
 
-constexpr int kFTB = 32;    // boundary rows per pass
+constexpr int kFTB = 64;    // boundary rows per pass
 constexpr int kFNB = 20;    // stencil slots per boundary row: only inward offsets couple, 3^(dim-1) * spacedim <= 18
 
 __global__ void __launch_bounds__(256, 4)
@@ -58,6 +58,7 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
     }
     __syncthreads();
     const int nbd = sNb;
+    const int nbd_pad = (nbd + 31) & ~31;
     const int lgn = __ffs(cP.n) - 1;
     for (int t0 = 0; t0 < nbd; t0 += kFTB) {
       const int nt = min(kFTB, nbd - t0);
@@ -141,7 +142,8 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int rb = r0 + u * rows_per_pass;
-            if (rb < kFTB) *reinterpret_cast<double2 *>(W + (size_t)(t0 + rb) * lay.ldx + 2 * c2) = acc[u];
+            if (rb < kFTB && t0 + rb < nbd_pad)   // W holds round_up(nbd, 32) rows: dense_mma streams tiles of 32
+              *reinterpret_cast<double2 *>(W + (size_t)(t0 + rb) * lay.ldx + 2 * c2) = acc[u];
           }
         }
       }
