@@ -1,11 +1,12 @@
 // k_patch_flux : W = S_b X_i - P_b, the boundary flux of every candidate before the M^{-1} scaling
 // (B_full - PT_boundary of source/LOD.cc:609-617; S_boundary = A[boundary, internal] :520-528 is applied matrix free).
 //
-// One CTA per patch, 32 boundary rows per pass: the compact stencil rows towards interior dofs are assembled by the
-// warps, the gather  W[b, :] = sum_e A[b, e] X[e, :]  reads X through L1 (this kernel keeps shared memory small on
-// purpose: several CTAs per SM and a large L1 turn the 9-fold reuse of every X row into cache hits), then the
-// projection weights of the at most 2^dim coarse cells containing the boundary dof are subtracted.  Rows are written
-// in ascending boundary-dof order, zero padded to a multiple of 32 rows, for k_patch_dense_mma to stream.
+// One CTA per patch, 64 boundary rows per pass: the compact stencil rows towards interior dofs are assembled by the
+// warps, the gather  W[b, :] = sum_e A[b, e] X[e, :]  reads X through L1 and writes the rows straight to W (a warp
+// covers 512 contiguous bytes), then the projection weights of the at most 2^dim coarse cells containing the boundary
+// dof are subtracted by a read-modify-write of the rows just written.  No staging tile: 18 KB of shared memory, four
+// CTAs per SM and a large L1 that turns the 9-fold reuse of every X row into cache hits; two barriers per pass.
+// Rows are in ascending boundary-dof order, zero padded to a multiple of 32 rows, for k_patch_dense_mma to stream.
 // Included by kernels.cu.
 #pragma once
 
