@@ -58,6 +58,40 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Sums of N (4 or 8) per-lane values over the warp with N + log2(32 / N) + ... shuffles instead of 5 N: at every
+// butterfly step a lane keeps one half of its values and hands the other half to its partner.  Afterwards lane L holds
+// the total of index warp_sum_index<N>(L) (the four lanes of a quad hold the same one).  Fixed order: deterministic.
+template <int N>
+__device__ __forceinline__ int warp_sum_index(int lane) {
+  return (N == 8) ? (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1)
+                  : (((lane >> 4) & 1) << 1) | ((lane >> 3) & 1);
+}
+__device__ __forceinline__ double warp_sum_packed(const double (&a)[8], int lane) {
+  const bool h4 = (lane >> 4) & 1, h3 = (lane >> 3) & 1, h2 = (lane >> 2) & 1;
+  double v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    v[j] = (h4 ? a[4 + j] : a[j]) + __shfl_xor_sync(0xffffffffu, h4 ? a[j] : a[4 + j], 16);
+  double w[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) w[j] = (h3 ? v[2 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, h3 ? v[j] : v[2 + j], 8);
+  double x = (h2 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w[0] : w[1], 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x;
+}
+__device__ __forceinline__ double warp_sum_packed(const double (&a)[4], int lane) {
+  const bool h4 = (lane >> 4) & 1, h3 = (lane >> 3) & 1;
+  double v[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    v[j] = (h4 ? a[2 + j] : a[j]) + __shfl_xor_sync(0xffffffffu, h4 ? a[j] : a[2 + j], 16);
+  double x = (h3 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, h3 ? v[0] : v[1], 8);
+  x += __shfl_xor_sync(0xffffffffu, x, 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x;
+}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -548,17 +582,15 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            acc[u] = warp_sum((xa[u].x * cc[0] + xa[u].y * cc[1]) + (xb[u].x * cc[2] + xb[u].y * cc[3]));
-          if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (r0 + u < g.Ni) {
-                sPhi[sRowDof[r0 + u]] = acc[u];
-                nrm += acc[u] * acc[u];
-              }
-            }
+            acc[u] = (xa[u].x * cc[0] + xa[u].y * cc[1]) + (xb[u].x * cc[2] + xb[u].y * cc[3]);
+          const double tot = warp_sum_packed(acc, lane);   // lane L holds row r0 + warp_sum_index<8>(L)
+          const int r = r0 + warp_sum_index<8>(lane);
+          if ((lane & 3) == 0 && r < g.Ni) {
+            sPhi[sRowDof[r]] = tot;
+            nrm += tot * tot;
           }
         }
+        nrm = warp_sum(nrm);
       } else {
         // generic layout (SIMT solver): four rows per warp iteration, scalar loads
         for (int r0 = 4 * warp; r0 < g.Ni; r0 += 4 * nwarp) {
@@ -828,14 +860,11 @@ k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi,
             }
           }
         }
-#pragma unroll
-        for (int k = 0; k < NA; ++k) acc[k] = warp_sum(acc[k]);
-        if (lane < NA) {
-          // lane k writes pair (member k / S, component k % S)
-          double val = 0.0;
-#pragma unroll
-          for (int k = 0; k < NA; ++k) val = (lane == k) ? acc[k] : val;
-          const int mem = lane / S, d = lane - mem * S;
+        const double val = warp_sum_packed(acc, lane);   // lane L holds pair warp_sum_index<NA>(L)
+        if ((lane & (NA == 8 ? 3 : 7)) == 0) {
+          // pair k = (member k / S, component k % S)
+          const int k = warp_sum_index<NA>(lane);
+          const int mem = k / S, d = k - mem * S;
           if (sGeo[mem][7]) {
             const int Dx = qc[0] - sGeo[mem][3], Dy = qc[1] - sGeo[mem][4], Dz = (DIM == 3) ? qc[2] - sGeo[mem][5] : 0;
             if (abs(Dx) <= w && abs(Dy) <= w && abs(Dz) <= w) {
