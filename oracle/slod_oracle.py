@@ -634,13 +634,19 @@ class SlodOracle:
         C = sp.csc_matrix((np.concatenate(v_phi), (rows, cols)), shape=(n_fine, n_coarse))
         AC = sp.csc_matrix((np.concatenate(v_aphi), (rows, cols)), shape=(n_fine, n_coarse))
         ones = sp.csc_matrix((np.ones(rows.shape), (rows, cols)), shape=(n_fine, n_coarse))
+        return self.galerkin_product(C, AC, ones), C, AC
+
+    @staticmethod
+    def galerkin_product(C, AC, ones):
+        """K = C^T (A C) on the structural pattern of the sparse product (source/LOD.cc:970-971: Tmmult of the two
+        Trilinos matrices): (i, j) is an entry iff columns i and j of C store a common row -- stored zeros count.
+        `ones` has the stored pattern of C with all values 1."""
         Kv = (C.T @ AC).tocsr()
         pattern = (ones.T @ ones).tocsr()   # structural product pattern (explicit zeros of C are entries)
         pattern.sort_indices()
         r, c = pattern.nonzero()
-        K = sp.csr_matrix((np.asarray(Kv[r, c]).ravel(), pattern.indices.copy(), pattern.indptr.copy()),
-                          shape=pattern.shape)
-        return K, C, AC
+        return sp.csr_matrix((np.asarray(Kv[r, c]).ravel(), pattern.indices.copy(), pattern.indptr.copy()),
+                             shape=pattern.shape)
 
     # -- fine right-hand side used by Poisson_LOD_Example (f = 1, zero Dirichlet rows) ------------
     def fem_rhs_constant_one(self):

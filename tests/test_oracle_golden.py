@@ -119,6 +119,92 @@ def test_poisson_lod_example(golden_dir):
     assert K.shape == (16, 16)
 
 
+def test_fe_q_iso_q1_02_elasticity_cell_matrix(golden_dir):
+    """tests/fe_q_iso_q1_02.cc: the vector-valued Q_iso_Q1(3) cell matrix of 2 eps(u):eps(v) + div u div v assembled by the
+    reference's sub-cell loops (include/Elasticity.h:211-284) equals the plain FEValues double loop; the test prints the
+    tolerance it passed with (1e-16).  Here: the oracle's sub-cell assembly (lambda = mu = 1) against an independent
+    evaluation with global hat functions at every iterated Gauss point."""
+    tol = float(_read(golden_dir, "fe_q_iso_q1_02.output").split()[0])
+    assert tol == 1e-16
+    n = 3
+    prob = SlodProblem(dim=2, spacedim=2, n_global_refinements=0, n_subdivisions=n, oversampling=0, stabilize=False,
+                       problem="elasticity", coefficients=[CoefficientTable(2, 0, np.ones(1)), CoefficientTable(2, 0, np.ones(1))])
+    o = SlodOracle(prob)
+    shape, lo = o.shape_for((0, 0))
+    A = o.assemble_patch_stiffness(shape, lo).toarray()          # dof = 2 * node + comp, nodes x fastest
+    # independent: hat functions of the (n+1)^2 node grid, 2-point Gauss rule iterated n times per axis
+    G = n + 1
+    h = 1.0 / n
+    nodes1 = np.arange(G) * h
+
+    def hat(x):            # values and derivatives of the G one-dimensional hats at x
+        v = np.maximum(0.0, 1.0 - np.abs(x - nodes1) / h)
+        d = np.where(np.abs(x - nodes1) < h, -np.sign(x - nodes1) / h, 0.0)
+        return v, d
+
+    g1 = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+    pts = np.concatenate([(c + g1) * h for c in range(n)])
+    ref = np.zeros((2 * G * G, 2 * G * G))
+    for y in pts:
+        vy, dy = hat(y)
+        for x in pts:
+            vx, dx = hat(x)
+            gx = np.outer(vy, dx).ravel()          # d/dx of node (ix, iy), index iy * G + ix
+            gy = np.outer(dy, vx).ravel()
+            w = (h / 2.0) ** 2
+            # u = phi e_c: eps = sym(grad), div = d_c phi
+            grads = {0: (gx, gy), 1: (gx, gy)}
+            for ci in range(2):
+                for cj in range(2):
+                    # 2 eps_i : eps_j for unit vectors e_ci, e_cj
+                    if ci == cj:
+                        other = gy if ci == 0 else gx
+                        same = gx if ci == 0 else gy
+                        e2 = 2.0 * np.outer(same, same) + np.outer(other, other)
+                    else:
+                        gi_other = gy if ci == 0 else gx      # d_{cj} phi_i
+                        gj_other = gy if cj == 0 else gx      # d_{ci} phi_j
+                        e2 = np.outer(gi_other, gj_other)
+                    di = gx if ci == 0 else gy
+                    dj = gx if cj == 0 else gy
+                    ref[ci::2, cj::2] += (e2 + np.outer(di, dj)) * w
+    assert np.abs(A - ref).max() <= 50 * tol * max(1.0, np.abs(ref).max())
+    assert np.abs(A - A.T).max() <= 50 * tol
+
+
+def test_assembly_01_entries(golden_dir):
+    """tests/assembly_01.cc: 1-D, 6 cells of FE_Q_iso_Q1(4), indicator basis (a shared vertex belongs to both cells),
+    all-ones cell matrices: the printed entries of A_lod = C^T A C (an early prototype of the coarse assembly: the
+    entries (i, i+-2) come from A coupling the two shared vertices of the cell in between)."""
+    import scipy.sparse as sp
+    entries = {}
+    for line in _read(golden_dir, "assembly_01.output").splitlines():
+        m = re.match(r"\((\d+),(\d+)\) (\S+)", line.strip())
+        if m:
+            entries[(int(m.group(1)), int(m.group(2)))] = float(m.group(3))
+    assert len(entries) == 24
+    ncell, deg = 6, 4
+    nf = ncell * deg + 1
+    cell_dofs = [np.arange(c * deg, c * deg + deg + 1) for c in range(ncell)]
+    A = np.zeros((nf, nf))
+    C = np.zeros((nf, ncell))
+    for c, dofs in enumerate(cell_dofs):
+        A[np.ix_(dofs, dofs)] += 1.0
+        C[dofs, c] = 1.0
+    Kd = C.T @ A @ C
+    got = {(i, j): float(Kd[i, j]) for i in range(ncell) for j in range(ncell) if Kd[i, j] != 0.0}
+    assert got == entries
+    # The oracle's scatter-and-product keeps the pattern of Tmmult(C, AC) with AC stored on C's pattern (what
+    # LOD::assemble_global_matrix does, source/LOD.cc:933-971): columns sharing a stored row, here |i - j| <= 1.
+    Cs = sp.csc_matrix(C)
+    AC = sp.csc_matrix(np.where(C != 0.0, A @ C, 0.0))
+    K = SlodOracle.galerkin_product(Cs, AC, Cs)
+    K.sort_indices()
+    for i in range(ncell):
+        cols = K.indices[K.indptr[i]:K.indptr[i + 1]]
+        assert list(cols) == [j for j in range(ncell) if abs(i - j) <= 1]
+
+
 def test_online_restatement_consistency():
     """fem_rhs (Gauss quadrature) reproduces the closed form for f = 1 and integrates a linear f exactly; the oracle's
     CG + SSOR(1.2) (LOD::solve, source/LOD.cc:991-998) agrees with the direct branch (source/LOD.cc:984-989)."""
