@@ -37,7 +37,7 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
     const double *X = Xbuf + (size_t)w * lay.x_stride;
     double *W = Wbuf + (size_t)w * lay.w_stride;
     __syncthreads();
-    load_coef(geo, d_coef, sCoef);
+    if (tid >= 32) load_coef(geo, d_coef, sCoef, tid - 32, NT - 32);   // beside warp 0's serial list building
     if (tid < 32) {  // boundary dofs (patch boundary, id 99), ascending
       int count = 0;
       for (int base = 0; base < geo.nnodes; base += 32) {

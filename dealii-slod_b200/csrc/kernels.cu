@@ -30,7 +30,9 @@ cudaError_t upload_params(const Params &p) { return cudaMemcpyToSymbol(cP, &p, s
 __device__ __forceinline__ int nfields() { return cP.problem == 0 ? 1 : 2; }
 
 // copy the patch's sub-cell coefficients (window origin g.clo) into shared memory, field-major
-__device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, double *sCoef) {
+// t0 / nt: index and number of the threads taking part (default: the whole CTA)
+__device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, double *sCoef, int t0 = -1, int nt = 0) {
+  if (t0 < 0) { t0 = threadIdx.x; nt = blockDim.x; }
   const int n = cP.n;
   const int msx = g.m[0] * n, msy = g.m[1] * n, msz = (cP.dim == 3) ? g.m[2] * n : 1;
   const int nsubp = msx * msy * msz;
@@ -38,7 +40,7 @@ __device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, doub
   const long long fstride = (cP.dim == 3) ? nsub * nsub * nsub : nsub * nsub;
   const int nf = nfields();
   const int nq = cP.gauss_coef ? (1 << cP.dim) : 1;   // values per sub-cell
-  for (int idx = threadIdx.x; idx < nf * nsubp * nq; idx += blockDim.x) {
+  for (int idx = t0; idx < nf * nsubp * nq; idx += nt) {
     const int q = idx % nq;
     int r = idx / nq;
     const int f = r / nsubp;
@@ -51,6 +53,29 @@ __device__ void load_coef(const Geom &g, const double *__restrict__ d_coef, doub
                     gz = (cP.dim == 3) ? (long long)g.clo[2] * n + oz : 0;
     sCoef[idx] = d_coef[(f * fstride + (gz * nsub + gy) * nsub + gx) * nq + q];
   }
+}
+
+// Morton code of a cell by bit dilation (same value as morton_encode of geom.h, a dozen instructions instead of a loop
+// over dim * ref bits)
+__device__ __forceinline__ unsigned dilate2(unsigned x) {
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ unsigned dilate3(unsigned x) {
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__device__ __forceinline__ unsigned morton_fast(const int c[3], int dim) {
+  return (dim == 3) ? (dilate3(c[0]) | (dilate3(c[1]) << 1) | (dilate3(c[2]) << 2))
+                    : (dilate2(c[0]) | (dilate2(c[1]) << 1));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -823,7 +848,7 @@ k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi,
 #pragma unroll
       for (int a = 0; a < DIM; ++a) inside = inside && (qc[a] >= 0 && qc[a] < cP.N);
       if (!inside) continue;
-      const int qid = (int)morton_encode(qc, DIM, cP.ref);
+      const int qid = (int)morton_fast(qc, DIM);
       const Geom gq = make_geom_at(cP, qc);
       // sweep box = box(q) /\ common box, in global node coordinates
       int b0[3], b1[3];

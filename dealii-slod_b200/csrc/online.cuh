@@ -91,36 +91,13 @@ k_prolongate(long long n_fine, const double *__restrict__ phi, const double *__r
       for (c[1] = c0[1]; c[1] <= c1[1]; ++c[1])
         for (c[0] = c0[0]; c[0] <= c1[0]; ++c[0]) {
           const Geom g = make_geom_at(cP, c);
-          const int pid = (int)morton_encode(c, dim, cP.ref);
+          const int pid = (int)morton_fast(c, dim);
           const int loc[3] = {a[0] - g.lo[0] * n, a[1] - g.lo[1] * n, a[2] - g.lo[2] * n};
           const int li = node_index(g, loc) * s + comp;
           for (int d = 0; d < s; ++d) acc += u[(size_t)pid * s + d] * phi[((size_t)pid * s + d) * nf_max + li];
         }
     u_fine[idx] = acc;
   }
-}
-
-// Morton code of a cell by bit dilation (same value as morton_encode of geom.h, a dozen instructions instead of a loop
-// over dim * ref bits: the column index is computed for every entry of every matrix-vector product)
-__device__ __forceinline__ unsigned dilate2(unsigned x) {
-  x &= 0xffffu;
-  x = (x | (x << 8)) & 0x00ff00ffu;
-  x = (x | (x << 4)) & 0x0f0f0f0fu;
-  x = (x | (x << 2)) & 0x33333333u;
-  x = (x | (x << 1)) & 0x55555555u;
-  return x;
-}
-__device__ __forceinline__ unsigned dilate3(unsigned x) {
-  x &= 0x3ffu;
-  x = (x | (x << 16)) & 0x030000ffu;
-  x = (x | (x << 8)) & 0x0300f00fu;
-  x = (x | (x << 4)) & 0x030c30c3u;
-  x = (x | (x << 2)) & 0x09249249u;
-  return x;
-}
-__device__ __forceinline__ unsigned morton_fast(const int c[3], int dim) {
-  return (dim == 3) ? (dilate3(c[0]) | (dilate3(c[1]) << 1) | (dilate3(c[2]) << 2))
-                    : (dilate2(c[0]) | (dilate2(c[1]) << 1));
 }
 
 // ---- conjugate gradients on the block-ELL coarse matrix ----
