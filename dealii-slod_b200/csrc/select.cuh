@@ -24,6 +24,30 @@ constexpr int kEigLd = 36;    // row stride of the candidate block (== 4 mod 16:
 // item = w * s + d  (w: index in the chunk's work list, d: component)
 __device__ __forceinline__ int sym_idx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
+// c = M^{-1} (e_d + sum_k z_k e_other[k])  (source/LOD.cc:727-743): eight rows of M^{-1} per warp pass (their loads are
+// in flight together) and one packed reduction for the eight sums
+__device__ __forceinline__ void minv_times_selection(const double *__restrict__ Minv, const double *z, int ncd, int n,
+                                                     int d, double *__restrict__ cv, int warp, int nwarp, int lane) {
+  for (int i0 = 0; i0 < ncd; i0 += 8 * nwarp) {
+    double acc[8];
+    const double *row[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc[u] = 0.0;
+      row[u] = Minv + (size_t)min(i0 + warp + nwarp * u, ncd - 1) * ncd;   // rows past the end: loaded, not stored
+    }
+    for (int k = lane; k < n; k += 32) {
+      const double zk = z[k];
+      const int col = k + (k >= d);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += zk * row[u][col];
+    }
+    const double tot = warp_sum_packed(acc, lane);   // lane L holds row index warp_sum_index<8>(L)
+    const int i = i0 + warp + nwarp * warp_sum_index<8>(lane);
+    if ((lane & 3) == 0 && i < ncd) cv[i] = Minv[i * ncd + d] + tot;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_select_fast
 // ------------------------------------------------------------------------------------------------
@@ -206,12 +230,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
         }
         __syncthreads();
         if (sFlag) {
-          for (int i = warp; i < ncd; i += NWARP) {
-            double acc = 0.0;
-            for (int k = lane; k < n; k += 32) acc += sz[k] * Minv[i * ncd + (k + (k >= d))];
-            acc = warp_sum(acc);
-            if (lane == 0) cv[i] = Minv[i * ncd + d] + acc;
-          }
+          minv_times_selection(Minv, sz, ncd, n, d, cv, warp, NWARP, lane);
           done = true;
         }
       }
@@ -628,13 +647,7 @@ k_eig_finish(const int *__restrict__ patch_ids, int *__restrict__ counters, cons
       if (tid == 0) jac_list[atomicAdd(&counters[2], 1)] = it;
       continue;
     }
-    // c = M^{-1} (e_d + sum_k d_k e_other[k])  (source/LOD.cc:727-743)
-    for (int i = warp; i < ncd; i += (NT >> 5)) {
-      double acc = 0.0;
-      for (int k = lane; k < n; k += 32) acc += sd[k] * Minv[i * ncd + (k + (k >= d))];
-      acc = warp_sum(acc);
-      if (lane == 0) cv[i] = Minv[i * ncd + d] + acc;
-    }
+    minv_times_selection(Minv, sd, ncd, n, d, cv, warp, NT >> 5, lane);
     if (tid == 0) {
       // smallest singular value still in use
       double kept = sig0;
