@@ -8,12 +8,15 @@
  * called from LOD::run() (source/LOD.cc:1433-1434), together with the integer set-up they depend on
  * (create_patches source/LOD.cc:122-244, create_mesh_for_patch :770-858, fill_dofs_indices_vector
  * include/LODtools.h:334-375) and the PDE hook assemble_stiffness (include/Diffusion.h:111-207,
- * include/Elasticity.h:163-299).  INTEGRATION.md shows the reference-side binding.
+ * include/Elasticity.h:163-299).  On top of those two, the stages that consume their results are exported as well
+ * (SURVEY section 8f rows 1-2): LOD::solve() and the prolongation (source/LOD.cc:975-1001, :1251), the fine FEM reference
+ * solve and the error norms (source/LOD.cc:1004-1094, :1252).  INTEGRATION.md shows the reference-side binding.
  *
  * Conventions
  *  - plain C, opaque handle, no exceptions cross the boundary; every call returns an int status
  *    (SLOD_OK == 0) and slod_last_error() gives the message of the last failure on that handle.
  *  - all floating point data is fp64; all buffers are caller-owned.
+ *  - calls return when their results are complete, with one exception: slod_assemble_coarse only enqueues (see there).
  *  - one handle drives ONE CUDA device (one process per GPU; the collective between ranks is done
  *    by the caller on the device buffers, see slod_*_device entry points).
  *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
@@ -46,7 +49,7 @@ enum {
   SLOD_ERR_UNSUPPORTED = 2,  /* configuration outside the implemented envelope           */
   SLOD_ERR_CUDA = 3,         /* CUDA runtime error or no usable device                   */
   SLOD_ERR_STATE = 4,        /* call order violated (e.g. basis requested before compute) */
-  SLOD_ERR_NUMERIC = 5       /* a patch problem was not SPD / eigen-solver did not converge */
+  SLOD_ERR_NUMERIC = 5       /* a patch problem was not SPD / an eigen-solver or CG did not converge */
 };
 
 enum { SLOD_PROBLEM_DIFFUSION = 0, SLOD_PROBLEM_ELASTICITY = 1 };
