@@ -40,7 +40,7 @@ WORKLOADS = {
     "diffusion2d_16c_l2_n2": dict(dim=2, s=1, ref=4, n=2, ell=2, r=5, kind="uniform100", seed=1234),
 }
 DEFAULT_WORKLOAD = "diffusion3d_32c_l2_n2"
-FP64_PEAK_TFLOPS = 37.2   # measured on this pool's B200 with tools/fp64_peak.cu (mma.sync m8n8k4 f64; DFMA 36.3)
+FP64_PEAK_FALLBACK = 37.2   # only if the in-run probe fails: measured earlier on this pool's B200 (mma.sync m8n8k4 f64; DFMA 36.3)
 
 
 def make_tables(w):
@@ -130,53 +130,59 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port on the host cores
+# CPU baseline / reference arm: the C++ restatement of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------------
-_ORC = None
+def cpu_sample_ids(w, block):
+    """One Morton-contiguous block of 1 / 2^dim of the patches (an octant of the 32^3 mesh = 4096 patches at cfg 4):
+    the same mix of interior / face / edge / corner patches as the whole mesh, and a compact set whose coarse-matrix
+    rows mostly stay inside the block."""
+    n = n_total(w)
+    nb = 2 ** w["dim"]
+    size = max(1, n // nb)
+    b = block % nb
+    return np.arange(b * size, min(n, (b + 1) * size), dtype=np.int64)
 
 
-def _orc_patch(pid):
-    res = _ORC.compute_patch(pid)
-    return float(res.basis[0] @ res.basis_premultiplied[0])
+def cpu_port_step(w, tables, block):
+    """One bounded sample of the offline phase on the host cores, through the C-ABI of the C++ port
+    (oracle/cpu/slod_cpu.cc, all hardware threads): handle set-up, coefficient upload, every stage of
+    LOD::compute_basis_function_candidates (source/LOD.cc:296-768) for the patches of one block, and the rows of
+    LOD::assemble_global_matrix (source/LOD.cc:860-973) of those patches (columns inside the block).
+    Returns (patches/s, seconds, handle, ids)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from cpu_port import CpuSlod
+    ids = cpu_sample_ids(w, block)
+    t0 = time.perf_counter()
+    cpu = CpuSlod(dim=w["dim"], spacedim=w["s"], n_global_refinements=w["ref"], n_subdivisions=w["n"],
+                  oversampling=w["ell"], stabilize=True, problem=0 if w["s"] == 1 else 1)
+    for f, t in enumerate(tables):
+        cpu.set_coefficient(f, w["r"], t)
+    cpu.compute_patches(ids)
+    cpu.assemble_coarse_subset()
+    dt = time.perf_counter() - t0
+    return ids.size / dt, dt, cpu, ids
 
 
-def cpu_oracle_rate(w, tables, n_sample, cores):
-    """patches/s of the oracle port on `cores` processes over an evenly spread sample of patch ids.
-    The integer patch structures (the oracle's stand-in for deal.II's per-patch Triangulation/DoFHandler
-    set-up) are built before the clock starts and inherited by the forked workers."""
-    global _ORC
-    import multiprocessing as mp
-    import threadpoolctl
-    from oracle.slod_oracle import CoefficientTable, SlodOracle, SlodProblem, morton_decode
-    n_patches = (2 ** w["ref"]) ** w["dim"]
-    pids = [int(x) for x in np.linspace(0, n_patches - 1, n_sample).astype(np.int64)]
-    with threadpoolctl.threadpool_limits(1):   # one BLAS thread per worker: the pool already uses every core
-        prob = SlodProblem(dim=w["dim"], spacedim=w["s"], n_global_refinements=w["ref"], n_subdivisions=w["n"],
-                           oversampling=w["ell"], stabilize=True,
-                           problem="diffusion" if w["s"] == 1 else "elasticity",
-                           coefficients=[CoefficientTable(w["dim"], w["r"], t) for t in tables])
-        _ORC = SlodOracle(prob)
-        for pid in pids:
-            _ORC.shape_for(morton_decode(pid, w["dim"], w["ref"]))
-        ctxm = mp.get_context("fork")
-        with ctxm.Pool(cores) as pool:
-            pool.map(_orc_patch, pids[:cores], chunksize=1)   # start the workers, touch LAPACK once
-            t0 = time.perf_counter()
-            pool.map(_orc_patch, pids, chunksize=1)
-            dt = time.perf_counter() - t0
-    return n_sample / dt, dt
+def cpu_sample_text(w, n_ids, cores):
+    return (f"{n_ids} patches per step = one Morton-contiguous 1/{2 ** w['dim']} block of the {n_total(w)} patches "
+            f"(block index rotates with the step); C++ restatement of source/LOD.cc:296-768 + :860-973 "
+            f"(oracle/cpu/slod_cpu.cc: banded Cholesky, Householder+QL eigen-solver, std::thread over patches, {cores} "
+            "threads), timed region = handle set-up + coefficient upload + basis + coarse-matrix rows of the block; "
+            "the deal.II/Trilinos reference itself cannot be built in this image")
 
 
 def run_reference(args, w, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     tables = make_tables(w)
-    per_step = max(cores * 32, 64)
     rates = []
+    cores = os.cpu_count() or 1
+    n_ids = 0
     for it in range(args.warmup + args.steps):
-        rate, dt = cpu_oracle_rate(w, tables, per_step, cores)
+        rate, dt, cpu, ids = cpu_port_step(w, tables, it)
+        cores, n_ids = cpu.threads, ids.size
+        cpu.close()
         if it >= args.warmup:
             rates.append((rate, dt))
     value = float(np.mean([r for r, _ in rates]))
@@ -186,12 +192,57 @@ def run_reference(args, w, wname):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_of(w, wname),
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} patches per step spread evenly over the {n_total(w)} patch ids; "
-                                   "numpy/scipy oracle (deal.II/Trilinos reference cannot be built here), one process per core"},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port", "language": "c++",
+                         "sample": cpu_sample_text(w, n_ids, cores)},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def parity_against_cpu(w, cpu, ids, phi_dev, aphi_dev, gpu_csr, diag_of):
+    """GPU results against the C++ CPU port on the sample of the CPU baseline (outside every timed region):
+    per-patch ||phi_gpu - phi_cpu||_2 (both have unit norm), the same for A phi relative to ||A phi||, truncation step
+    counts, and the coarse-matrix entries of the sample rows on the sample columns relative to max |K|."""
+    import scipy.sparse as sp
+    s = w["s"]
+    errs, aerrs, steps_bad, interior = [], [], 0, []
+    N, ell = 2 ** w["ref"], w["ell"]
+    for pid in ids:
+        pid = int(pid)
+        nf = cpu.patch_info(pid)["n_fine"]
+        c = [0] * w["dim"]
+        for b in range(w["ref"]):
+            for a in range(w["dim"]):
+                c[a] |= ((pid >> (w["dim"] * b + a)) & 1) << b
+        interior.append(all(ell <= x <= N - 1 - ell for x in c))
+        for d in range(s):
+            pc, ac = cpu.basis(pid, d)
+            pg = phi_dev[pid, d, :nf].cpu().numpy()
+            ag = aphi_dev[pid, d, :nf].cpu().numpy()
+            errs.append(float(np.linalg.norm(pg - pc)))
+            aerrs.append(float(np.linalg.norm(ag - ac) / np.linalg.norm(ac)))
+            steps_bad += int(cpu.diagnostics(pid, d)[1]) != int(diag_of(pid, d)[1])
+    errs, aerrs = np.array(errs), np.array(aerrs)
+    interior = np.repeat(np.array(interior), s)
+    out = {"against": "oracle/cpu/slod_cpu.cc (C++ CPU port) on the cpu_baseline sample", "n_patches": int(len(ids)),
+           "phi_max": float(errs.max()), "phi_p99": float(np.quantile(errs, 0.99)), "phi_median": float(np.median(errs)),
+           "phi_frac_le_1e-10": float((errs <= 1e-10).mean()),
+           "phi_max_full_size_patches": float(errs[interior].max()) if interior.any() else None,
+           "n_full_size_patches": int(interior.sum()),
+           "aphi_rel_max": float(aerrs.max()), "truncation_step_mismatches": int(steps_bad)}
+    if gpu_csr is not None:
+        rowptr, col, val = gpu_csr
+        n = rowptr.size - 1
+        Kg = sp.csr_matrix((val, col, rowptr), shape=(n, n))
+        rp, cc, vv = cpu.coarse_csr()
+        Kc = sp.csr_matrix((vv, cc, rp), shape=(n, n))
+        rows = (np.asarray(ids)[:, None] * s + np.arange(s)[None, :]).ravel()
+        sub_g = Kg[rows][:, rows]
+        sub_c = Kc[rows][:, rows]
+        kmax = float(np.abs(val).max())
+        out["K_rel_max"] = float(np.abs((sub_g - sub_c)).max() / kmax)
+        out["K_entries_compared"] = int(sub_c.nnz)
+    return out
 
 
 def n_total(w):
@@ -250,18 +301,18 @@ def main():
     tk = np.zeros(8)
 
     def run_basis(p0, p1):
-        ctx.compute_basis_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), stream)
-        tk[:4] = ctx.timings()[:4]
+        ctx.compute_basis_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), stream)    # enqueues only
 
     def run_coarse(p0, p1):
         ctx.assemble_coarse_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), stream)
-        tk[4] = ctx.timings()[4]
 
-    job = part.DistributedOffline(dist, rank, world, n, s, phi, aphi, K, run_basis, run_coarse)
+    job = part.DistributedOffline(dist, rank, world, n, s, phi, aphi, K, run_basis, run_coarse,
+                                  synchronize=ctx.synchronize)
     p0, p1 = job.p0, job.p1
 
     def step():
-        job.step()
+        job.step()            # ends with slod_synchronize: the step's status check, as a caller would do it
+        tk[:5] = ctx.timings()[:5]
         return tk.copy()
 
     def barrier():
@@ -304,8 +355,8 @@ def main():
                     ctx.set_coefficient(f, w["r"], tb)
                 ctx.compute_basis()
                 ctx.assemble_coarse()            # enqueues; the basis read-back below overlaps the coarse kernels
-                ph, aph = ctx.all_basis()
-                rowptr, col, val = ctx.coarse_csr()
+                ph, aph = ctx.all_basis(reuse=True)
+                rowptr, col, val = ctx.coarse_csr(reuse=True)
                 e2e_bytes[0] = val.nbytes + ph.nbytes + aph.nbytes
                 return float(val[0] + ph[0, 0, 0])
             e2e_bytes = [0]
@@ -368,6 +419,35 @@ def main():
                   "u_fine_l2": float(np.linalg.norm(uh)),
                   "note": "host-buffer C ABI calls (copies included), forcing f = 1, diag(K)-preconditioned CG"}
 
+    # ---- N > 1: the distributed result against a single-GPU recomputation on rank 0 (outside the timed region) ----
+    multi_gpu_check = None
+    if world > 1:
+        job.step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            # patches of a sub-range that straddles the first partition boundary, recomputed by this rank alone into
+            # fresh buffers; the coarse rows of the range need A*phi of their neighbours: take it from the gathered array
+            half = max(1, min(64, (job.ranges[0][1] - job.ranges[0][0]) // 2))
+            q0, q1 = job.ranges[0][1] - half, min(n, job.ranges[0][1] + half)
+            phi2 = torch.zeros_like(phi)
+            aphi2 = torch.zeros_like(aphi)
+            ctx.compute_basis_device(q0, q1, phi2.data_ptr(), aphi2.data_ptr(), stream)
+            ctx.synchronize()
+            same_phi = bool(torch.equal(phi2[q0:q1], phi[q0:q1]))
+            same_aphi = bool(torch.equal(aphi2[q0:q1], aphi[q0:q1]))
+            K2 = torch.zeros_like(K)
+            ctx.assemble_coarse_device(q0, q1, phi.data_ptr(), aphi.data_ptr(), K2.data_ptr(), stream)
+            ctx.synchronize()
+            same_K = bool(torch.equal(K2[q0 * s:q1 * s], K[q0 * s:q1 * s]))
+            multi_gpu_check = {"range": [int(q0), int(q1)], "phi_bit_equal": same_phi, "aphi_bit_equal": same_aphi,
+                               "K_rows_bit_equal": same_K,
+                               "note": "rank 0 recomputes patches on both sides of the first partition boundary on its own "
+                                       "and compares with the all-gathered result"}
+            if not (same_phi and same_aphi and same_K):
+                raise SystemExit(f"multi-GPU result differs from the single-GPU recomputation: {multi_gpu_check}")
+            del phi2, aphi2, K2
+        barrier()
+
     if rank == 0:
         fm = flop_model(w)
         names = ["patch_solve", "patch_dense", "patch_select", "patch_finish"]
@@ -379,31 +459,51 @@ def main():
         kern["coarse"] = {"ms": float(kms[4])}
         dom = max(names, key=lambda nm: kms[names.index(nm)])
         achieved = kern[dom]["tflops"]
-        kname = {"patch_solve": "k_patch_solve_mma", "patch_dense": "k_patch_dense_mma",
+        kname = {"patch_solve": "k_patch_solve_mma", "patch_dense": "k_patch_flux + k_patch_dense_mma",
                  "patch_select": "k_select_fast + k_eig_tridiag/ql/finish", "patch_finish": "k_patch_finish"}[dom]
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")   # per-launch DRAM bytes from the committed ncu capture
         if os.path.exists(tfile) and args.workload == DEFAULT_WORKLOAD and world == 1:
-            traffic = json.load(open(tfile)).get(kname)
+            traffic = json.load(open(tfile)).get(kname.split(" ")[0])
+        # FP64 peak of THIS device, measured now (same process, after the timed region) with the library's probe kernels
+        peak, peak_src = FP64_PEAK_FALLBACK, "fallback constant (probe failed)"
+        try:
+            with ClockSampler(local) as pclk:
+                dfma, dmma = ctx.measure_fp64_peak()
+            peak = max(dfma, dmma)
+            peak_src = (f"slod_measure_fp64_peak in this run: DFMA {dfma:.2f}, mma.sync m8n8k4 f64 {dmma:.2f} TFLOP/s "
+                        f"at {pclk.summary()['sm_mhz']} MHz (MEASURED_PEAKS.json has no fp64 entry)")
+        except Exception as exc:   # noqa: BLE001
+            peak_src += f": {exc}"
         roofline = {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe on B200)", "kernel": kname,
-                    "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-                    "traffic": traffic,
-                    "peak_source": "measured here by tools/fp64_peak.cu (MEASURED_PEAKS.json has no fp64 entry)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
                     "flop_model": "banded Cholesky Ni*bw^2 + 4*Ni*bw*Ncd per patch (SURVEY 8d), summed over actual patch shapes",
                     "kernels": kern}
+        for nm in kern:
+            if "tflops" in kern[nm]:
+                kern[nm]["frac"] = kern[nm]["tflops"] / peak
         cpu = None
+        parity = None
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            ns = max(cores * 32, 64)
-            rate, dt = cpu_oracle_rate(w, tables, ns, cores)
-            cpu = {"value": rate, "unit": "patches/s", "cores": cores, "kind": "port",
-                   "sample": f"{ns} patches spread evenly over the patch ids ({dt:.1f} s), numpy/scipy oracle, one process per core"}
+            rate, dt, cpu_h, ids = cpu_port_step(w, tables, 0)
+            cpu = {"value": rate, "unit": "patches/s", "cores": cpu_h.threads, "kind": "port", "language": "c++",
+                   "seconds": dt, "sample": cpu_sample_text(w, ids.size, cpu_h.threads)}
+            # the same patches from the GPU run, compared outside the timed region
+            step()
+            gpu_csr = None
+            if e2e is not None:
+                ctx.compute_basis()
+                ctx.assemble_coarse()
+                gpu_csr = ctx.coarse_csr(reuse=True)
+            parity = parity_against_cpu(w, cpu_h, ids, phi, aphi, gpu_csr, lambda pid, d: ctx.diagnostics(pid, d))
+            cpu_h.close()
         line = {"metric": "slod_basis_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_of(w, args.workload), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "offline_wall_ms": ms_step, "online": online}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_max": parity,
+                "multi_gpu_check": multi_gpu_check, "offline_wall_ms": ms_step, "online": online}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@ EXPORTS = [
     "slod_get_patch_diagnostics", "slod_debug_patch_stages", "slod_get_timings", "slod_compute_basis_device",
     "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
     "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
-    "slod_fem_solve", "slod_fine_norms",
+    "slod_fem_solve", "slod_fine_norms", "slod_synchronize", "slod_measure_fp64_peak",
 ]
 
 
@@ -43,18 +43,20 @@ class SlodError(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 
 
-def load_library():
-    """Load libslod_b200.so (built in-tree by ``__graft_entry__.build()``); fails loudly when absent."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+def load_library(path=None):
+    """Load libslod_b200.so (built in-tree by ``__graft_entry__.build()``); fails loudly when absent.
+    ``path``: another implementation of include/slod.h -- only the test / baseline infrastructure passes one (the C++
+    CPU restatement under oracle/); symbols such a library does not export raise AttributeError when called."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the CUDA library is the product; there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = _Lib(C.CDLL(path), partial=(path != LIB_PATH))
     P = C.POINTER
     vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
     lib.slod_create.argtypes = [P(SlodParams), P(vp)]
@@ -92,20 +94,63 @@ def load_library():
     lib.slod_launch_count.argtypes = [vp, P(i64)]
     lib.slod_alloc_host.argtypes = [C.c_size_t, P(vp)]
     lib.slod_free_host.argtypes = [vp]
-    _lib = lib
+    lib.slod_synchronize.argtypes = [vp]
+    lib.slod_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
+    _libs[path] = lib
     return lib
+
+
+class _Missing:
+    """Stand-in for a symbol a partial implementation of slod.h does not export: declaring its signature is a no-op,
+    calling it fails."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a):
+        raise AttributeError(f"this library does not export {self._name}")
+
+
+class _Lib:
+    def __init__(self, cdll, partial):
+        object.__setattr__(self, "_cdll", cdll)
+        object.__setattr__(self, "_partial", partial)   # the product library must export everything: strict
+        object.__setattr__(self, "_missing", {})
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._cdll, name)
+        except AttributeError:
+            if not self._partial or not name.startswith("slod_"):
+                raise
+            return self._missing.setdefault(name, _Missing(name))
 
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+class _PinnedBlock:
+    """Owner of one slod_alloc_host block; numpy arrays made from it keep it alive through their ``base`` chain and the
+    block is released by slod_free_host when the last of them is collected."""
+
+    def __init__(self, lib, addr, nbytes):
+        self._lib, self._addr = lib, addr
+        self.__array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (addr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._lib.slod_free_host(C.c_void_p(self._addr))
+        except Exception:
+            pass
+
+
 class SlodContext:
     """Thin object wrapper over the opaque ``slod_ctx`` handle."""
 
     def __init__(self, dim=2, spacedim=1, n_global_refinements=2, n_subdivisions=2, oversampling=1,
-                 stabilize=False, problem=PROBLEM_DIFFUSION, quirk_presaved=False, device=-1):
-        self.lib = load_library()
+                 stabilize=False, problem=PROBLEM_DIFFUSION, quirk_presaved=False, device=-1, lib=None):
+        self.lib = load_library(lib)
         self.par = SlodParams(dim, spacedim, n_global_refinements, n_subdivisions, oversampling,
                               int(bool(stabilize)), problem, int(bool(quirk_presaved)), device)
         self.h = C.c_void_p()
@@ -115,30 +160,32 @@ class SlodContext:
         self.dim, self.s = dim, spacedim
 
     def close(self):
-        for ptr in getattr(self, "_pinned_ptrs", []):
-            self.lib.slod_free_host(ptr)
-        self._pinned_ptrs, self._pinned = [], {}
+        """Destroy the handle.  Arrays returned earlier stay valid: each owns its page-locked block (see _out)."""
+        self._reuse = {}
         if getattr(self, "h", None) and self.h.value:
             self.lib.slod_destroy(self.h)
             self.h = C.c_void_p()
 
-    def _out(self, key, shape, dtype=np.float64):
-        """Output array in page-locked memory (slod_alloc_host), allocated once per key and reused by later calls."""
-        if not hasattr(self, "_pinned"):
-            self._pinned, self._pinned_ptrs = {}, []
+    def _out(self, key, shape, dtype=np.float64, reuse=False):
+        """Output array in page-locked memory (slod_alloc_host).  The array owns its block: the block is freed when the
+        last view of it is garbage collected, never by close().  reuse=False (default): a fresh block per call, so
+        results of earlier calls are never overwritten.  reuse=True: the block of the previous call with the same key
+        and shape is handed out again (benchmark loops; the caller accepts that the earlier array is overwritten)."""
+        if not hasattr(self, "_reuse"):
+            self._reuse = {}
         shape = tuple(int(x) for x in np.atleast_1d(shape))
-        arr = self._pinned.get(key)
-        if arr is not None and arr.shape == shape and arr.dtype == dtype:
-            return arr
+        if reuse:
+            arr = self._reuse.get(key)
+            if arr is not None and arr.shape == shape and arr.dtype == dtype:
+                return arr
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         ptr = C.c_void_p()
         if self.par.device == -2 or self.lib.slod_alloc_host(nbytes, C.byref(ptr)) != SLOD_OK:
             arr = np.empty(shape, dtype=dtype)                       # maps-only handle / allocation refused
         else:
-            self._pinned_ptrs.append(ptr)
-            buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
-            arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        self._pinned[key] = arr
+            arr = np.asarray(_PinnedBlock(self.lib, ptr.value, nbytes)).view(dtype)[: int(np.prod(shape))].reshape(shape)
+        if reuse:
+            self._reuse[key] = arr
         return arr
 
     def __del__(self):
@@ -220,22 +267,22 @@ class SlodContext:
         self._ck(self.lib.slod_basis_stride(self.h, C.byref(n)))
         return n.value
 
-    def all_basis(self):
+    def all_basis(self, reuse=False):
         shape = (self.n_patches, self.s, self.basis_stride)
-        phi = self._out("phi", shape)
-        aphi = self._out("aphi", shape)
+        phi = self._out("phi", shape, reuse=reuse)
+        aphi = self._out("aphi", shape, reuse=reuse)
         self._ck(self.lib.slod_get_all_basis(self.h, _dp(phi), _dp(aphi)))
         return phi, aphi
 
     def assemble_coarse(self):
         self._ck(self.lib.slod_assemble_coarse(self.h))
 
-    def coarse_csr(self):
+    def coarse_csr(self, reuse=False):
         nr, nnz = C.c_int64(), C.c_int64()
         self._ck(self.lib.slod_get_coarse_csr(self.h, None, None, None, C.byref(nr), C.byref(nnz)))
-        rowptr = self._out("rowptr", nr.value + 1, np.int64)
-        col = self._out("col", nnz.value, np.int64)
-        val = self._out("val", nnz.value)
+        rowptr = self._out("rowptr", nr.value + 1, np.int64, reuse=reuse)
+        col = self._out("col", nnz.value, np.int64, reuse=reuse)
+        val = self._out("val", nnz.value, reuse=reuse)
         i64p = C.POINTER(C.c_int64)
         self._ck(self.lib.slod_get_coarse_csr(self.h, rowptr.ctypes.data_as(i64p), col.ctypes.data_as(i64p),
                                               _dp(val), C.byref(nr), C.byref(nnz)))
@@ -335,6 +382,16 @@ class SlodContext:
     def assemble_coarse_device(self, p0, p1, d_phi, d_aphi, d_K, stream=0):
         self._ck(self.lib.slod_assemble_coarse_device(self.h, p0, p1, C.c_void_p(d_phi), C.c_void_p(d_aphi),
                                                       C.c_void_p(d_K), C.c_void_p(stream)))
+
+    def synchronize(self):
+        """Wait for the device-buffer calls above; raises SlodError (SLOD_ERR_NUMERIC) if a patch reported a status."""
+        self._ck(self.lib.slod_synchronize(self.h))
+
+    def measure_fp64_peak(self):
+        """(DFMA, DMMA) TFLOP/s of the handle's device, measured now."""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.slod_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def ell_to_csr(self, h_K):
         h_K = np.ascontiguousarray(h_K, dtype=np.float64)

@@ -51,6 +51,8 @@ struct slod_ctx {
   bool basis_done = false, coarse_done = false;
   // chunk workspaces
   int chunk = 0;
+  bool chunk_limited = false;
+  int64_t ids_cap = 0;   // capacity of d_ids (patches of one range)
   int *d_ids = nullptr;
   double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr, *d_W = nullptr;
   FluxLayout xl{};
@@ -72,6 +74,11 @@ struct slod_ctx {
   int grid_solve = 0, grid_dense = 0, grid_finish = 0, grid_coarse = 0;
   int bw_max = 0, nb_max = 0;
   cudaEvent_t ev[10]{};
+  std::vector<cudaEvent_t> chunk_ev;   // 5 per chunk of the last run_basis
+  size_t chunks_pending = 0;
+  bool basis_pending = false;
+  int64_t pending_p0 = 0, pending_p1 = 0;
+  int *h_status = nullptr;   // page-locked copy of d_status
   Timings tm;
   int64_t launches = 0;
   std::vector<int> ids;   // cost-sorted work list of the last patch range
@@ -245,15 +252,15 @@ int check_patch(const slod_ctx *ctx, int64_t patch) {
   return SLOD_OK;
 }
 
+void free_workspace(slod_ctx *c);
 void free_dev(slod_ctx *c) {
   auto F = [](auto *&p) {
     if (p) cudaFree(p);
     p = nullptr;
   };
   F(c->d_coef); F(c->d_phi); F(c->d_aphi); F(c->d_Kell); F(c->d_diag); F(c->d_status);
-  F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
   F(c->d_perm); F(c->d_val); F(c->d_online);
-  F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
+  free_workspace(c);
 }
 
 // Expand the caller's tables (problem_parameter::value, include/Diffusion.h:40-53) onto the fine sub-cell
@@ -307,29 +314,51 @@ int prepare_coefficients(slod_ctx *ctx) {
   return SLOD_OK;
 }
 
+void free_workspace(slod_ctx *c) {
+  auto F = [](auto *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
+  F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
+  c->chunk = 0;
+  c->ids_cap = 0;
+}
+
+// Per-patch workspaces for `chunk` patches at a time and the work list of a whole range.  The chunk is sized for the
+// range actually computed (a rank of an N-GPU run owns 1/N of the patches), capped by half of the free memory; a later
+// call with a larger range reallocates.  ctx->chunk is committed only after every allocation has succeeded: a failed
+// allocation leaves the handle without a workspace (chunk == 0) instead of with dangling null pointers.
+// SLOD_CHUNK (environment) forces a small chunk: the multi-chunk loop is exercised by tests/test_parity_gpu.py.
 int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   const Params &P = ctx->P;
-  if (ctx->chunk > 0) return SLOD_OK;
+  n_range = std::max<int64_t>(1, std::min<int64_t>(n_range, ctx->n_patches));
   const size_t per_patch = ((size_t)ctx->sl.x_stride + 2 * (size_t)ctx->dl.m_stride + (size_t)P.s * P.NcdMax +
                             (ctx->dense_ntile ? (size_t)ctx->xl.w_stride : 0)) * 8 + 4;
+  int64_t forced = 0;
+  if (const char *env = getenv("SLOD_CHUNK")) forced = std::max(1, atoi(env));
+  if (ctx->chunk > 0 && ctx->ids_cap >= n_range && (ctx->chunk >= n_range || ctx->chunk_limited)) return SLOD_OK;
+  cudaStreamSynchronize(0);
+  cudaDeviceSynchronize();   // the old workspace may still be in use by enqueued kernels
+  free_workspace(ctx);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = std::min<size_t>(free_b / 2, (size_t)96 << 30);   // one chunk for 2^15 3-D patches (53 GB) on a 180 GB part
-  int64_t chunk = std::max<int64_t>(1, (int64_t)(budget / per_patch));
-  (void)n_range;
-  chunk = std::min<int64_t>(chunk, ctx->n_patches);
-  ctx->chunk = (int)chunk;
-  CK(cudaMalloc(&ctx->d_ids, sizeof(int) * chunk));
-  CK(cudaMalloc(&ctx->d_counter, sizeof(int) * 4));
-  CK(cudaMalloc(&ctx->d_work_counter, sizeof(int) * 4));
-  CK(cudaMalloc(&ctx->d_X, sizeof(double) * (size_t)ctx->sl.x_stride * chunk));
-  CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
-  CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
-  CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
-  if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
-  CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
-  // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
-  {
+  const size_t budget = std::min<size_t>(free_b / 2, (size_t)96 << 30);   // one chunk for 2^15 3-D patches (53 GB) on a 180 GB part
+  int64_t by_mem = std::max<int64_t>(1, (int64_t)(budget / per_patch));
+  int64_t chunk = std::min<int64_t>(by_mem, n_range);
+  if (forced) chunk = std::min<int64_t>(chunk, forced);
+  const bool limited = chunk < n_range;   // memory- or environment-limited: a larger range would not get a larger chunk
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&ctx->d_ids, sizeof(int) * n_range));
+    CK(cudaMalloc(&ctx->d_counter, sizeof(int) * 4));
+    CK(cudaMalloc(&ctx->d_work_counter, sizeof(int) * 4));
+    CK(cudaMalloc(&ctx->d_X, sizeof(double) * (size_t)ctx->sl.x_stride * chunk));
+    CK(cudaMalloc(&ctx->d_Minv, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
+    CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
+    CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
+    if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
+    CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
+    // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
     SelectPlan &sp = ctx->sp;
     SelectBuffers &sb = ctx->sb;
     const size_t items = (size_t)chunk * P.s;
@@ -349,10 +378,24 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
       CK(cudaMalloc(&sb.rot_n, sizeof(int) * 2 * cap));
       sp.grid_ql = (int)std::min<size_t>((cap + 7) / 8, (size_t)ctx->n_sm * 8);
     }
+    return SLOD_OK;
+  };
+  const int rc = body();
+  if (rc != SLOD_OK) {
+    free_workspace(ctx);
+    cudaGetLastError();
+    return rc;
   }
+  ctx->chunk = (int)chunk;
+  ctx->chunk_limited = limited;
+  ctx->ids_cap = n_range;
+  ctx->ids_p0 = ctx->ids_p1 = -1;   // the work list on the device went with the old buffer
   return SLOD_OK;
 }
 
+// Enqueues stages assembly .. premultiply for the patches [p0, p1) on `st` and returns without waiting: the work list
+// of the whole range is uploaded once, every chunk has its own timing events, the status words of the range are cleared
+// in front of the kernels and copied to page-locked host memory behind them.  wait_basis() is the synchronisation point.
 int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_aphi, cudaStream_t st) {
   const Params &P = ctx->P;
   if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
@@ -362,7 +405,7 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
   rc = ensure_workspace(ctx, p1 - p0);
   if (rc) return rc;
   CK(upload_params(P));
-  // work order: largest patches first (integer geometry: cached per range)
+  // work order: largest patches first (integer geometry: cached per range, on the host and on the device)
   if (ctx->ids_p0 != p0 || ctx->ids_p1 != p1) {
     std::vector<int> order((size_t)(p1 - p0));
     std::iota(order.begin(), order.end(), (int)p0);
@@ -376,55 +419,89 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     ctx->ids.resize(order.size());
     for (size_t i = 0; i < perm.size(); ++i) ctx->ids[i] = order[perm[i]];
+    CK(cudaMemcpyAsync(ctx->d_ids, ctx->ids.data(), sizeof(int) * ctx->ids.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // pageable source: the vector may be rebuilt by the next call
     ctx->ids_p0 = p0;
     ctx->ids_p1 = p1;
   }
-  const std::vector<int> &ids = ctx->ids;
+  const size_t n_ids = ctx->ids.size();
+  if (!ctx->h_status) CK(cudaHostAlloc(&ctx->h_status, sizeof(int) * (size_t)ctx->n_patches, cudaHostAllocDefault));
+  CK(cudaMemsetAsync(ctx->d_status + p0, 0, sizeof(int) * (size_t)(p1 - p0), st));
 
   static const bool static_stride = getenv("SLOD_STATIC_WORK") != nullptr;   // A/B switch of the work distribution
   int *wc = static_stride ? nullptr : ctx->d_work_counter;
-  float acc[4] = {0, 0, 0, 0};
-  for (size_t off = 0; off < ids.size(); off += ctx->chunk) {
-    const int nw = (int)std::min<size_t>(ctx->chunk, ids.size() - off);
-    CK(cudaMemcpyAsync(ctx->d_ids, ids.data() + off, sizeof(int) * nw, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[0], st));
+  const size_t n_chunks = (n_ids + ctx->chunk - 1) / ctx->chunk;
+  while (ctx->chunk_ev.size() < 5 * n_chunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    ctx->chunk_ev.push_back(e);
+  }
+  ctx->chunks_pending = 0;
+  for (size_t off = 0, ci = 0; off < n_ids; off += ctx->chunk, ++ci) {
+    const int nw = (int)std::min<size_t>(ctx->chunk, n_ids - off);
+    const int *ids = ctx->d_ids + off;
+    cudaEvent_t *ev = ctx->chunk_ev.data() + 5 * ci;
+    CK(cudaEventRecord(ev[0], st));
     if (ctx->mma_variant >= 0)
-      CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw,
+      CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx,
                                 ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw, wc));
     else
-      CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+      CK(launch_patch_solve(std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Lws, ctx->d_status, ctx->sl));
-    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaEventRecord(ev[1], st));
     if (ctx->dense_ntile) {
-      CK(launch_patch_flux(std::min(nw, ctx->grid_flux), ctx->smem_flux, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+      CK(launch_patch_flux(std::min(nw, ctx->grid_flux), ctx->smem_flux, st, ids, nw, ctx->d_coef, ctx->d_X,
                            ctx->d_W, ctx->xl, wc));
-      CK(launch_patch_dense_mma(ctx->dense_ntile, std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw,
+      CK(launch_patch_dense_mma(ctx->dense_ntile, std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_W, ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status,
                                 ctx->dl, wc));
       ctx->launches += 1;
     }
     else
-      CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ctx->d_ids, nw, ctx->d_coef, ctx->d_X,
+      CK(launch_patch_dense(std::min(nw, ctx->grid_dense), ctx->smem_dense, st, ids, nw, ctx->d_coef, ctx->d_X,
                             ctx->d_Minv, ctx->d_G, ctx->d_diag, ctx->d_status, ctx->dl));
-    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaEventRecord(ev[2], st));
     int nl = 0;
-    CK(launch_select_pipeline(ctx->sp, st, ctx->d_ids, nw, ctx->d_Minv, ctx->d_G, ctx->d_cvec, ctx->d_diag,
+    CK(launch_select_pipeline(ctx->sp, st, ids, nw, ctx->d_Minv, ctx->d_G, ctx->d_cvec, ctx->d_diag,
                               ctx->d_status, ctx->sb, &nl));
     ctx->launches += nl;
-    CK(cudaEventRecord(ctx->ev[3], st));
-    CK(launch_patch_finish(std::min(nw, ctx->grid_finish), ctx->smem_finish, st, ctx->d_ids, nw, ctx->d_coef,
+    CK(cudaEventRecord(ev[3], st));
+    CK(launch_patch_finish(std::min(nw, ctx->grid_finish), ctx->smem_finish, st, ids, nw, ctx->d_coef,
                            ctx->d_X, ctx->d_cvec, d_phi, d_aphi, ctx->fl));
-    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaEventRecord(ev[4], st));
     ctx->launches += 3;
-    CK(cudaEventSynchronize(ctx->ev[4]));  // ids buffer is reused by the next chunk
+    ++ctx->chunks_pending;
+  }
+  CK(cudaMemcpyAsync(ctx->h_status + p0, ctx->d_status + p0, sizeof(int) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[7], st));
+  ctx->basis_pending = true;
+  ctx->pending_p0 = p0;
+  ctx->pending_p1 = p1;
+  return SLOD_OK;
+}
+
+// Synchronisation point of run_basis: waits for the range, adds up the per-chunk stage times and maps the status words
+// of the range to SLOD_ERR_NUMERIC (first offending patch in the message).
+int wait_basis(slod_ctx *ctx) {
+  if (!ctx->basis_pending) return SLOD_OK;
+  ctx->basis_pending = false;
+  CK(cudaEventSynchronize(ctx->ev[7]));
+  float acc[4] = {0, 0, 0, 0};
+  for (size_t ci = 0; ci < ctx->chunks_pending; ++ci)
     for (int k = 0; k < 4; ++k) {
       float ms = 0;
-      CK(cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));
+      CK(cudaEventElapsedTime(&ms, ctx->chunk_ev[5 * ci + k], ctx->chunk_ev[5 * ci + k + 1]));
       acc[k] += ms;
     }
-  }
   for (int k = 0; k < 4; ++k) ctx->tm.ms[k] = acc[k];
+  for (int64_t i = ctx->pending_p0; i < ctx->pending_p1; ++i)
+    if (ctx->h_status[i]) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "patch %lld: numerical status bits 0x%x (1 A_ii not SPD, 2 M not SPD, 4 Jacobi not converged)",
+               (long long)i, ctx->h_status[i]);
+      return fail(ctx, SLOD_ERR_NUMERIC, buf);
+    }
   return SLOD_OK;
 }
 
@@ -628,6 +705,10 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     // shapes are products of per-axis extents; scanning the patches along the diagonal + full scan for small grids
     for (int64_t pid = 0; pid < ctx->n_patches; ++pid) {
       const Geom g = make_geom(P, (int)pid);
+      if (g.Ni <= 0) {   // n_subdivisions = 1 on a one-cell patch: no interior dof, the patch problem is empty
+        delete ctx;
+        return bad(SLOD_ERR_UNSUPPORTED, "a patch has no interior fine dof (n_subdivisions = 1 with one-cell patches)");
+      }
       bw_max = std::max(bw_max, g.bw);
       int nb = 0;
       // patch-boundary dofs
@@ -804,6 +885,8 @@ void slod_destroy(slod_ctx *ctx) {
   free_dev(ctx);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   delete ctx;
 }
 
@@ -812,9 +895,11 @@ int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const dou
   NEED_DEVICE();
   const Params &P = ctx->P;
   if (field < 0 || field >= ctx->n_fields) return fail(ctx, SLOD_ERR_INVALID, "coefficient field index out of range");
-  if (eta_refinement < 0 || eta_refinement > 15) return fail(ctx, SLOD_ERR_INVALID, "eta_refinement out of range");
-  const int nl = 1 << eta_refinement;
-  if ((size_t)ipow(nl, P.dim) != n) return fail(ctx, SLOD_ERR_INVALID, "coefficient table size != (2^r)^dim");
+  if (eta_refinement < 0 || eta_refinement * P.dim > 30)
+    return fail(ctx, SLOD_ERR_INVALID, "eta_refinement out of range ((2^r)^dim must stay below 2^31)");
+  size_t want = 1;
+  for (int a = 0; a < P.dim; ++a) want <<= eta_refinement;
+  if (want != n) return fail(ctx, SLOD_ERR_INVALID, "coefficient table size != (2^r)^dim");
   ctx->coef_table[field].assign(cellwise, cellwise + n);
   ctx->coef_r[field] = eta_refinement;
   ctx->coef_set[field] = true;
@@ -969,7 +1054,7 @@ int slod_assemble_coarse_device(slod_ctx *ctx, int64_t p0, int64_t p1, const dou
   if (!ctx || !d_phi || !d_aphi || !d_K) return SLOD_ERR_INVALID;
   NEED_DEVICE();
   CK(cudaSetDevice(ctx->device));
-  return run_coarse(ctx, p0, p1, d_phi, d_aphi, d_K, (cudaStream_t)stream);
+  return run_coarse(ctx, p0, p1, d_phi, d_aphi, d_K, (cudaStream_t)stream, false);   // enqueue only, see slod_synchronize
 }
 
 int slod_compute_basis(slod_ctx *ctx) {
@@ -981,22 +1066,22 @@ int slod_compute_basis(slod_ctx *ctx) {
     CK(cudaMalloc(&ctx->d_phi, sizeof(double) * n));
     CK(cudaMalloc(&ctx->d_aphi, sizeof(double) * n));
   }
-  CK(cudaMemset(ctx->d_status, 0, sizeof(int) * ctx->n_patches));
+  ctx->basis_done = ctx->coarse_done = false;
   int rc = run_basis(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, 0);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
-  std::vector<int> st((size_t)ctx->n_patches);
-  CK(cudaMemcpy(st.data(), ctx->d_status, sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
+  rc = wait_basis(ctx);
+  if (rc) return rc;
   ctx->basis_done = true;
-  ctx->coarse_done = false;
-  for (size_t i = 0; i < st.size(); ++i)
-    if (st[i]) {
-      char buf[160];
-      snprintf(buf, sizeof buf, "patch %zu: numerical status bits 0x%x (1 A_ii not SPD, 2 M not SPD, 4 Jacobi not converged)",
-               i, st[i]);
-      return fail(ctx, SLOD_ERR_NUMERIC, buf);
-    }
   return SLOD_OK;
+}
+
+int slod_synchronize(slod_ctx *ctx) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  int rc = wait_basis(ctx);
+  if (rc) return rc;
+  return finish_coarse_timing(ctx);
 }
 
 int slod_get_basis(const slod_ctx *ctx, int64_t patch, int comp, double *phi, double *aphi) {
@@ -1354,9 +1439,12 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   CK(cudaSetDevice(ctx->device));
   rc = prepare_coefficients(ctx);
   if (rc) return rc;
+  rc = wait_basis(ctx);   // the workspace of an enqueued range is about to be reused
+  if (rc) return rc;
   rc = ensure_workspace(ctx, 1);
   if (rc) return rc;
   CK(upload_params(ctx->P));
+  ctx->ids_p0 = ctx->ids_p1 = -1;   // the device work list is overwritten below
   const int id = (int)patch;
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
   if (ctx->mma_variant >= 0)
@@ -1385,10 +1473,23 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   return SLOD_OK;
 }
 
+int slod_measure_fp64_peak(slod_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+  if (!ctx || !dfma_tflops || !dmma_tflops) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(run_fp64_probe(ctx->n_sm, dfma_tflops, dmma_tflops));
+  ctx->launches += 8;
+  return SLOD_OK;
+}
+
 int slod_get_timings(const slod_ctx *ctx, double *ms, int n) {
   if (!ctx || !ms) return SLOD_ERR_INVALID;
-  if (ctx->coarse_timing_pending && ctx->device != SLOD_DEVICE_NONE) {
-    int rc = finish_coarse_timing(const_cast<slod_ctx *>(ctx));
+  if (ctx->device != SLOD_DEVICE_NONE && (ctx->coarse_timing_pending || ctx->basis_pending)) {
+    slod_ctx *c = const_cast<slod_ctx *>(ctx);
+    int rc = wait_basis(c);   // a numerical status is reported here too: the times of a failed run mean nothing
+    if (rc) return rc;
+    rc = finish_coarse_timing(c);
     if (rc) return rc;
   }
   for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->tm.ms[i];

@@ -1161,6 +1161,70 @@ cudaError_t launch_fine_quadratic_form(cudaStream_t st, int op, long long n_node
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 throughput probes: the denominator of the roofline the benchmark reports (MEASURED_PEAKS.json has no fp64 entry).
+// Register-resident chains, 4 CTAs of 512 threads per SM: plain DFMA, and mma.sync m8n8k4 (the instruction of the
+// tensor-core kernels above).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) k_probe_dfma(double *out, int iters) {
+  double a[8];
+  const double b = 1.000000001, c = 1e-9;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(512) k_probe_dmma(double *out, int iters) {
+  double c[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+  const double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// returns TFLOP/s of the DFMA chain and of the DMMA chain on the current device
+cudaError_t run_fp64_probe(int n_sm, double *dfma_tflops, double *dmma_tflops) {
+  const int grid = n_sm * 4, block = 512, iters = 20000;
+  double *out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * grid * block);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const double threads = (double)grid * block, warps = threads / 32;
+  double best[2] = {0, 0};
+  for (int which = 0; which < 2; ++which)
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition = warm-up
+      cudaEventRecord(e0, 0);
+      if (which == 0) k_probe_dfma<<<grid, block>>>(out, iters);
+      else k_probe_dmma<<<grid, block>>>(out, iters);
+      cudaEventRecord(e1, 0);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double flop = (which == 0) ? threads * iters * 8 * 2.0 : warps * iters * 4 * (8 * 8 * 4 * 2.0);
+      if (rep > 0) best[which] = fmax(best[which], flop / (ms * 1e-3) / 1e12);
+    }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *dfma_tflops = best[0];
+  *dmma_tflops = best[1];
+  return cudaGetLastError();
+}
+
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay) {
   cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

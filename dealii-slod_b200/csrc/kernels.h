@@ -135,6 +135,7 @@ cudaError_t run_cg(cudaStream_t st, int nrows, const CgOperator &A, const double
                    long long *launches);
 cudaError_t launch_fine_quadratic_form(cudaStream_t st, int op, long long n_nodes, const double *d_coef, const double *x,
                                        double *partial, int *n_partial);
+cudaError_t run_fp64_probe(int n_sm, double *dfma_tflops, double *dmma_tflops);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);
 

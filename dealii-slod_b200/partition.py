@@ -51,13 +51,15 @@ class DistributedOffline:
     that fill the rows of the range in the shared-layout tensors ``phi``/``aphi`` ([n_patches, s, stride]) and ``K``
     ([n_patches * s, ell_width]); on a GPU they are the ``slod_*_device`` entry points, in the CPU tests an oracle."""
 
-    def __init__(self, dist, rank, world, n_patches, spacedim, phi, aphi, K, compute_basis, assemble_coarse):
+    def __init__(self, dist, rank, world, n_patches, spacedim, phi, aphi, K, compute_basis, assemble_coarse,
+                 synchronize=None):
         self.dist, self.rank, self.world = dist, rank, world
         self.ranges = all_ranges(n_patches, world)
         self.p0, self.p1 = self.ranges[rank]
         self.s = spacedim
         self.phi, self.aphi, self.K = phi, aphi, K
         self._basis, self._coarse = compute_basis, assemble_coarse
+        self._sync = synchronize    # slod_synchronize of the handle: the device entry points only enqueue
 
     def step(self, gather_K=True):
         self._basis(self.p0, self.p1)
@@ -65,3 +67,5 @@ class DistributedOffline:
         self._coarse(self.p0, self.p1)
         if gather_K:
             all_gather_rows(self.dist, self.K, self.ranges, self.rank, self.s)  # disjoint K row blocks
+        if self._sync is not None:
+            self._sync()     # numerical status of the range (SLOD_ERR_NUMERIC raises here)

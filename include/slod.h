@@ -16,7 +16,9 @@
  *  - plain C, opaque handle, no exceptions cross the boundary; every call returns an int status
  *    (SLOD_OK == 0) and slod_last_error() gives the message of the last failure on that handle.
  *  - all floating point data is fp64; all buffers are caller-owned.
- *  - calls return when their results are complete, with one exception: slod_assemble_coarse only enqueues (see there).
+ *  - host-buffer calls return when their results are complete, with one exception: slod_assemble_coarse only enqueues
+ *    (see there).  The device-buffer entry points (slod_*_device) only enqueue on the caller's stream;
+ *    slod_synchronize() is their synchronisation point and reports numerical failures of the enqueued patches.
  *  - one handle drives ONE CUDA device (one process per GPU; the collective between ranks is done
  *    by the caller on the device buffers, see slod_*_device entry points).
  *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
@@ -162,6 +164,10 @@ int slod_get_patch_diagnostics(const slod_ctx *ctx, int64_t patch, int comp, dou
  * X = A_ii^{-1} P_i  (n_internal x n_coarse, row-major), Minv (n_coarse^2), BD^T BD (n_coarse^2). Any may be NULL. */
 int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Minv, double *G);
 
+/* FP64 throughput of the handle's device in TFLOP/s, measured now with two register-resident probe kernels: a DFMA chain
+ * and an mma.sync.m8n8k4.f64 chain (the instruction of the tensor-core kernels).  The benchmark's roofline denominator. */
+int slod_measure_fp64_peak(slod_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+
 /* per-kernel device times of the last compute/assemble (CUDA events), ms:
  *   [0] patch solve  [1] dense (M, BD, Gram)  [2] selection (eigen)  [3] finish (phi, A phi)
  *   [4] coarse matrix  [5] H2D  [6] D2H  [7] total device */
@@ -178,6 +184,10 @@ int slod_compute_basis_device(slod_ctx *ctx, int64_t patch_begin, int64_t patch_
  * Needs d_phi of the range and d_A_phi of ALL patches (all-gathered by the caller). */
 int slod_assemble_coarse_device(slod_ctx *ctx, int64_t patch_begin, int64_t patch_end, const double *d_phi,
                                 const double *d_A_phi, double *d_K, void *stream);
+/* Synchronisation point of the two calls above: waits for what they enqueued, makes slod_get_timings valid and returns
+ * SLOD_ERR_NUMERIC (first offending patch in slod_last_error) if a patch of the last basis range reported a status
+ * (A_ii or M not positive definite, eigen-solver not converged) -- the same mapping slod_compute_basis does. */
+int slod_synchronize(slod_ctx *ctx);
 int slod_ell_width(const slod_ctx *ctx, int64_t *width);
 /* convert a host copy of the block-ELL matrix into CSR (same contract as slod_get_coarse_csr) */
 int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,

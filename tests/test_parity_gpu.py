@@ -197,3 +197,48 @@ def test_generic_fallback_kernels(env, case, monkeypatch):
     assert per_patch.max() <= 1e-4 and np.median(per_patch) <= 1e-11 and np.quantile(per_patch, 0.75) <= 1e-9
     assert np.abs(k - k_ref).max() <= 1e-3 * np.abs(k_ref).max()
     assert np.abs(a - a_ref).max() <= 1e-3 * np.abs(a_ref).max()
+
+
+def test_device_entry_reports_numerical_status():
+    """slod_compute_basis_device must surface the per-patch status bits.  A coefficient with negative
+    values makes A_ii indefinite on some patches; the failure arrives at slod_synchronize as SLOD_ERR_NUMERIC and a
+    clean run afterwards reports nothing (the bits of the range are cleared in front of the kernels)."""
+    import torch
+    ctx, _ = build_pair(dim=2, s=1, ref=3, n=2, ell=1, seed=3)
+    n, stride = ctx.n_patches, ctx.basis_stride
+    phi = torch.zeros((n, 1, stride), dtype=torch.float64, device="cuda")
+    aphi = torch.zeros_like(phi)
+    good = 1.0 + np.random.default_rng(3).random(64)
+    bad = good.copy()
+    bad[::3] = -5.0
+    ctx.set_coefficient(0, 3, bad)
+    ctx.compute_basis_device(0, n, phi.data_ptr(), aphi.data_ptr())
+    with pytest.raises(pkg.SlodError) as e:
+        ctx.synchronize()
+    assert e.value.code == 5 and "patch" in str(e.value)
+    with pytest.raises(pkg.SlodError):
+        ctx.compute_basis()          # the host-buffer path reports the same
+    ctx.set_coefficient(0, 3, good)
+    ctx.compute_basis_device(0, n, phi.data_ptr(), aphi.data_ptr())
+    ctx.synchronize()
+    assert torch.isfinite(phi).all()
+
+
+@pytest.mark.parametrize("case", [dict(dim=2, s=1, ref=4, n=2, ell=2), dict(dim=3, s=1, ref=2, n=2, ell=1)],
+                         ids=["2d", "3d"])
+def test_multi_chunk_loop(case, monkeypatch):
+    """n_patches > chunk: SLOD_CHUNK forces a workspace of 37 patches, so the range is processed
+    in several chunks that reuse the same buffers back to back; results must be bit-identical to the one-chunk run."""
+    ctx_ref, _ = build_pair(**case)
+    ctx_ref.compute_basis()
+    ctx_ref.assemble_coarse()
+    p_ref, a_ref = ctx_ref.all_basis()
+    k_ref = ctx_ref.coarse_csr()[2]
+    monkeypatch.setenv("SLOD_CHUNK", "37")
+    ctx, _ = build_pair(**case)
+    ctx.compute_basis()
+    ctx.assemble_coarse()
+    p, a = ctx.all_basis()
+    assert np.array_equal(p, p_ref) and np.array_equal(a, a_ref)
+    assert np.array_equal(ctx.coarse_csr()[2], k_ref)
+    assert ctx.timings()[0] > 0
