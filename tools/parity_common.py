@@ -66,15 +66,19 @@ def patch_tolerance(info, d, c=200.0):
 
 
 def margin_safe(info, d):
-    """False when a discontinuous decision of the reference rule is within rounding of flipping."""
+    """False when a discontinuous decision of the reference rule is within rounding of flipping: the computed d carries
+    an error of about eps * cond(G) * ||d||, so ||d||_inf within max(1e-8, 1e3 eps cond(G)) of the 0.5 threshold
+    (source/LOD.cc:703) can fall on either side in any fp64 implementation, LAPACK's included."""
     if not info.get("slod", False):
         return True
-    if abs(info["dinf"][d] - 0.5) <= 1e-3:
+    sig = np.asarray(info["sigma"][d])
+    kept = sig[sig > 1e-15 * sig[0]]
+    cond_full = float(sig[0] / kept[-1]) if len(kept) else 1.0
+    if abs(info["dinf"][d] - 0.5) <= max(1e-8, 1e3 * EPS * cond_full):
         return False
     # the singular-value threshold 1e-15 * sigma_0 (source/LOD.cc:667): a singular value of size ~eps * sigma_0 is
     # only known to O(1) relative accuracy, so a ratio within two decades of the threshold can fall on either side
     # (LAPACK's dgesdd included) and the selected d changes completely
-    sig = np.asarray(info["sigma"][d])
     ratio = sig / sig[0]
     return not np.any((ratio > 1e-17) & (ratio < 1e-13))
 
