@@ -312,7 +312,7 @@ def main():
 
     def step():
         job.step()            # ends with slod_synchronize: the step's status check, as a caller would do it
-        tk[:5] = ctx.timings()[:5]
+        tk[:6] = ctx.timings()[:6]
         return tk.copy()
 
     def barrier():
@@ -457,9 +457,12 @@ def main():
             if kms[i] > 0:
                 kern[nm] = {"ms": float(kms[i]), "tflops": fm[nm] * share / (kms[i] * 1e-3) / 1e12}
         kern["coarse"] = {"ms": float(kms[4])}
+        if kms[5] > 0:
+            kern["patch_solve"]["factor_ms"] = float(kms[5])
+            kern["patch_solve"]["trisolve_ms"] = float(kms[0] - kms[5])
         dom = max(names, key=lambda nm: kms[names.index(nm)])
         achieved = kern[dom]["tflops"]
-        kname = {"patch_solve": "k_patch_solve_mma", "patch_dense": "k_patch_flux + k_patch_dense_mma",
+        kname = {"patch_solve": "k_patch_factor + k_patch_trisolve" if kms[5] > 0 else "k_patch_solve_mma", "patch_dense": "k_patch_flux + k_patch_dense_mma",
                  "patch_select": "k_select_fast + k_eig_tridiag/ql/finish", "patch_finish": "k_patch_finish"}[dom]
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")   # per-launch DRAM bytes from the committed ncu capture

@@ -63,6 +63,11 @@ struct slod_ctx {
   int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
   int mma_threads = 0;
   int mma_nip = 0, mma_stw = 0;
+  bool split_solver = false;      // factor + triangular-solve kernels instead of the fused solver (large 3-D patches)
+  size_t smem_factor = 0, smem_tri = 0;
+  double *d_Lrec = nullptr;       // factor records of a chunk
+  cudaEvent_t ev_split = nullptr;
+  float split_factor_ms = 0;
   long long mma_lws_per_cta = 0;
   SolveLayout sl{};
   DenseLayout dl{};
@@ -320,6 +325,7 @@ void free_workspace(slod_ctx *c) {
     p = nullptr;
   };
   F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
+  F(c->d_Lrec);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
   c->chunk = 0;
   c->ids_cap = 0;
@@ -334,7 +340,8 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
   const Params &P = ctx->P;
   n_range = std::max<int64_t>(1, std::min<int64_t>(n_range, ctx->n_patches));
   const size_t per_patch = ((size_t)ctx->sl.x_stride + 2 * (size_t)ctx->dl.m_stride + (size_t)P.s * P.NcdMax +
-                            (ctx->dense_ntile ? (size_t)ctx->xl.w_stride : 0)) * 8 + 4;
+                            (ctx->dense_ntile ? (size_t)ctx->xl.w_stride : 0) +
+                            (ctx->split_solver ? (size_t)split_rec_stride(ctx->mma_nip) : 0)) * 8 + 4;
   int64_t forced = 0;
   if (const char *env = getenv("SLOD_CHUNK")) forced = std::max(1, atoi(env));
   if (ctx->chunk > 0 && ctx->ids_cap >= n_range && (ctx->chunk >= n_range || ctx->chunk_limited)) return SLOD_OK;
@@ -357,7 +364,10 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
     CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
     CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
     if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
-    CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
+    if (ctx->split_solver)
+      CK(cudaMalloc(&ctx->d_Lrec, sizeof(double) * (size_t)split_rec_stride(ctx->mma_nip) * chunk));
+    else
+      CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
     // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
     SelectPlan &sp = ctx->sp;
     SelectBuffers &sb = ctx->sb;
@@ -442,7 +452,14 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     const int *ids = ctx->d_ids + off;
     cudaEvent_t *ev = ctx->chunk_ev.data() + 5 * ci;
     CK(cudaEventRecord(ev[0], st));
-    if (ctx->mma_variant >= 0)
+    if (ctx->split_solver) {
+      CK(launch_patch_factor(std::min(nw, 2 * ctx->n_sm), ctx->smem_factor, st, ids, nw, ctx->d_coef, ctx->d_Lrec,
+                             ctx->d_status, ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
+      if (ci == 0) CK(cudaEventRecord(ctx->ev_split, st));
+      CK(launch_patch_trisolve(std::min(nw, ctx->n_sm), ctx->smem_tri, st, ids, nw, ctx->d_Lrec, ctx->d_X,
+                               ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
+      ctx->launches += 1;
+    } else if (ctx->mma_variant >= 0)
       CK(launch_patch_solve_mma(ctx->mma_variant, std::min(nw, ctx->grid_solve), ctx->smem_solve, st, ids, nw,
                                 ctx->d_coef, ctx->d_X, ctx->d_Lws, ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx,
                                 ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw, wc));
@@ -495,6 +512,11 @@ int wait_basis(slod_ctx *ctx) {
       acc[k] += ms;
     }
   for (int k = 0; k < 4; ++k) ctx->tm.ms[k] = acc[k];
+  if (ctx->split_solver && ctx->chunks_pending > 0) {   // first chunk: factorisation share of the solve stage
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->chunk_ev[0], ctx->ev_split));
+    ctx->tm.ms[5] = ms;
+  }
   for (int64_t i = ctx->pending_p0; i < ctx->pending_p1; ++i)
     if (ctx->h_status[i]) {
       char buf[160];
@@ -761,6 +783,11 @@ int slod_create(const slod_params *par, slod_ctx **out) {
       ctx->mma_nip = nip;
       ctx->mma_stw = P.s * ((P.dim == 3) ? 13 : 4) + P.s;
       ctx->smem_solve = solve_mma_smem(variant, coef_doubles, ctx->mma_nip, ctx->mma_stw);
+      if (variant == 0 && P.dim == 3 && P.s == 1 && P.problem == SLOD_PROBLEM_DIFFUSION && !getenv("SLOD_FUSED_SOLVER")) {
+        ctx->split_solver = true;
+        ctx->smem_factor = split_factor_smem(coef_doubles, nip);
+        ctx->smem_tri = split_trisolve_smem(nip);
+      }
     }
   }
   DenseLayout &dl = ctx->dl;
@@ -869,6 +896,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   cudaMemset(ctx->d_diag, 0, sizeof(double) * 8 * P.s * ctx->n_patches);
   for (auto &ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_bad("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev_split)) != cudaSuccess) return cuda_bad("cudaEventCreate", e);
   *out = ctx;
   return SLOD_OK;
 }
@@ -886,6 +914,7 @@ void slod_destroy(slod_ctx *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
+  if (ctx->ev_split) cudaEventDestroy(ctx->ev_split);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   delete ctx;
 }
@@ -1447,7 +1476,12 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   ctx->ids_p0 = ctx->ids_p1 = -1;   // the device work list is overwritten below
   const int id = (int)patch;
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
-  if (ctx->mma_variant >= 0)
+  if (ctx->split_solver) {
+    CK(launch_patch_factor(1, ctx->smem_factor, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_Lrec, ctx->d_status,
+                           ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, nullptr));
+    CK(launch_patch_trisolve(1, ctx->smem_tri, 0, ctx->d_ids, 1, ctx->d_Lrec, ctx->d_X, ctx->sl.coef_doubles,
+                             ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, nullptr));
+  } else if (ctx->mma_variant >= 0)
     CK(launch_patch_solve_mma(ctx->mma_variant, 1, ctx->smem_solve, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_X, ctx->d_Lws,
                               ctx->d_status, ctx->sl.coef_doubles, ctx->sl.ldx, ctx->sl.x_stride, ctx->mma_lws_per_cta, ctx->mma_nip, ctx->mma_stw));
   else

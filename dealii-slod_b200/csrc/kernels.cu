@@ -365,6 +365,7 @@ __device__ __forceinline__ void fetch_work_item(int w, int *work_counter, int *s
 }
 
 #include "solve_mma.cuh"
+#include "solve_split.cuh"
 namespace slod {
 
 // ------------------------------------------------------------------------------------------------
@@ -966,6 +967,38 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
     case 2: return launch_mma_t<4, 8>(grid, smem, st, ids, n_work, coef, X, Lws, status, lay, work_counter);
   }
   return cudaErrorInvalidValue;
+}
+
+// split solver (solve_split.cuh): factorisation with 8 warps, 2 CTAs per SM; triangular solves with 16 warps
+constexpr int kSplitRB = 13, kFactorWarps = 8, kTriWarps = 16;
+size_t split_factor_smem(int coef_doubles, int nip_max) {
+  const int R = 8 * kSplitRB, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * 64 + 64) +
+         sizeof(int) * ((size_t)nip_max + kSplitRB * (kSplitRB - 1) / 2 + 16 + 8);
+}
+size_t split_trisolve_smem(int nip_max) {
+  return sizeof(double) * ((size_t)kTriStages * kSplitRB * 64) + 2 * kTriStages * sizeof(unsigned long long) +
+         sizeof(int) * ((size_t)nip_max + 8 * kTriWarps + 8);
+}
+long long split_rec_stride(int nip_max) { return (long long)(nip_max / 8) * kSplitRB * 64; }
+cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                                double *Lrec, int *status, int coef_doubles, int nip_max, int ldx, long long x_stride,
+                                int *work_counter) {
+  SplitLayout lay{coef_doubles, nip_max, ldx, x_stride, split_rec_stride(nip_max)};
+  cudaError_t e = cudaFuncSetAttribute(k_patch_factor<kSplitRB, kFactorWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (work_counter && (e = cudaMemsetAsync(work_counter, 0, sizeof(int), st)) != cudaSuccess) return e;
+  k_patch_factor<kSplitRB, kFactorWarps><<<grid, 32 * kFactorWarps, smem, st>>>(ids, n_work, coef, Lrec, status, lay, work_counter);
+  return cudaGetLastError();
+}
+cudaError_t launch_patch_trisolve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Lrec,
+                                  double *X, int coef_doubles, int nip_max, int ldx, long long x_stride, int *work_counter) {
+  SplitLayout lay{coef_doubles, nip_max, ldx, x_stride, split_rec_stride(nip_max)};
+  cudaError_t e = cudaFuncSetAttribute(k_patch_trisolve<kSplitRB, kTriWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (work_counter && (e = cudaMemsetAsync(work_counter, 0, sizeof(int), st)) != cudaSuccess) return e;
+  k_patch_trisolve<kSplitRB, kTriWarps><<<grid, 32 * kTriWarps, smem, st>>>(ids, n_work, Lrec, X, lay, work_counter);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,

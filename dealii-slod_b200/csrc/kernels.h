@@ -59,6 +59,15 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
                                    const double *coef, double *X, double *Lws, int *status, int coef_doubles, int ldx,
                                    long long x_stride, long long lws_per_cta, int nip_max, int stw,
                                    int *work_counter = nullptr);
+// split solver for the large 3-D patches (solve_split.cuh): factor records in HBM, then the triangular solves
+size_t split_factor_smem(int coef_doubles, int nip_max);
+size_t split_trisolve_smem(int nip_max);
+long long split_rec_stride(int nip_max);
+cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
+                                double *Lrec, int *status, int coef_doubles, int nip_max, int ldx, long long x_stride,
+                                int *work_counter);
+cudaError_t launch_patch_trisolve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Lrec,
+                                  double *X, int coef_doubles, int nip_max, int ldx, long long x_stride, int *work_counter);
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                const double *X, double *Minv, double *G, double *diag, int *status,
                                const DenseLayout &lay);

@@ -170,7 +170,7 @@ int slod_measure_fp64_peak(slod_ctx *ctx, double *dfma_tflops, double *dmma_tflo
 
 /* per-kernel device times of the last compute/assemble (CUDA events), ms:
  *   [0] patch solve  [1] dense (M, BD, Gram)  [2] selection (eigen)  [3] finish (phi, A phi)
- *   [4] coarse matrix  [5] H2D  [6] D2H  [7] total device */
+ *   [4] coarse matrix  [5] factorisation share of [0] (split solver, first chunk)  [6], [7] reserved */
 int slod_get_timings(const slod_ctx *ctx, double *ms, int n);
 
 /* the hot path, device buffers (multi-GPU plumbing) ----------------------------------------------------*/

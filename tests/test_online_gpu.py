@@ -114,6 +114,15 @@ END_TO_END = [
     dict(dim=2, s=1, ref=4, n=2, ell=3, stabilize=False),
     dict(dim=2, s=2, ref=3, n=2, ell=1, stabilize=False),
     dict(dim=3, s=1, ref=2, n=2, ell=1, stabilize=False),
+    # SLOD branch.  With l = 1 the selection is well conditioned and the coarse vector agrees at
+    # 1e-9 too; with l = 2 the boundary patches' basis functions are only determined to ~1e-6 (cond(G) eps, see
+    # tests/test_fullsize_parity_gpu.py) and so is the coarse vector -- its coefficients refer to slightly different
+    # bases -- while the fine solution C u, the quantity the north star bounds, is insensitive: 1e-9 everywhere.
+    dict(dim=2, s=1, ref=4, n=2, ell=1, stabilize=True),
+    dict(dim=2, s=2, ref=3, n=2, ell=1, stabilize=True),
+    dict(dim=3, s=1, ref=2, n=2, ell=1, stabilize=True),
+    dict(dim=2, s=1, ref=4, n=2, ell=2, stabilize=True, coarse_tol=1e-5),
+    dict(dim=3, s=1, ref=3, n=2, ell=2, stabilize=True, coarse_tol=1e-5),
 ]
 
 
@@ -121,6 +130,8 @@ END_TO_END = [
 def test_solution_against_oracle(case):
     """Coarse and fine solution of the whole chain against the oracle's (reference preconditioner and direct solve):
     1e-9 relative, the north star's bound."""
+    case = dict(case)
+    coarse_tol = case.pop("coarse_tol", 1e-9)
     ctx, orc = build_pair(**case)
     s = case["s"]
     ctx.compute_basis()
@@ -133,10 +144,10 @@ def test_solution_against_oracle(case):
     u_dir, _ = orc.solve_coarse(K, b_ref, direct=True)
     assert np.linalg.norm(u_ssor - u_dir) <= 1e-9 * np.linalg.norm(u_dir)
     b = ctx.coarse_rhs(f)
-    assert np.linalg.norm(b - b_ref) <= 1e-10 * np.linalg.norm(b_ref)
+    assert np.linalg.norm(b - b_ref) <= max(1e-10, 0.1 * coarse_tol) * np.linalg.norm(b_ref)
     u, steps, _ = ctx.coarse_solve(b, max_steps=5000, tolerance=0.0, reduction=1e-13)
-    assert np.linalg.norm(u - u_dir) <= 1e-9 * np.linalg.norm(u_dir)
-    assert np.linalg.norm(u - u_ssor) <= 1e-9 * np.linalg.norm(u_dir)
+    assert np.linalg.norm(u - u_dir) <= coarse_tol * np.linalg.norm(u_dir)
+    assert np.linalg.norm(u - u_ssor) <= coarse_tol * np.linalg.norm(u_dir)
     uh = ctx.prolongate(u)
     uh_ref = C @ u_dir
     assert np.linalg.norm(uh - uh_ref) <= 1e-9 * np.linalg.norm(uh_ref)
