@@ -453,7 +453,8 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     cudaEvent_t *ev = ctx->chunk_ev.data() + 5 * ci;
     CK(cudaEventRecord(ev[0], st));
     if (ctx->split_solver) {
-      CK(launch_patch_factor(std::min(nw, 2 * ctx->n_sm), ctx->smem_factor, st, ids, nw, ctx->d_coef, ctx->d_Lrec,
+      static const int factor_grid_env = getenv("SLOD_FACTOR_GRID") ? atoi(getenv("SLOD_FACTOR_GRID")) : 0;   // experiments
+      CK(launch_patch_factor(std::min(nw, factor_grid_env > 0 ? factor_grid_env : 2 * ctx->n_sm), ctx->smem_factor, st, ids, nw, ctx->d_coef, ctx->d_Lrec,
                              ctx->d_status, ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
       if (ci == 0) CK(cudaEventRecord(ctx->ev_split, st));
       CK(launch_patch_trisolve(std::min(nw, ctx->n_sm), ctx->smem_tri, st, ids, nw, ctx->d_Lrec, ctx->d_X,
@@ -814,11 +815,14 @@ int slod_create(const slod_params *par, slod_ctx **out) {
       }
     }
   }
+  // the split solver keeps its columns in z-major order, which only the tensor-core flux / dense kernels understand
+  if (ctx->split_solver && !ctx->dense_ntile) ctx->split_solver = false;
   if (ctx->dense_ntile) {
     FluxLayout &xl = ctx->xl;
     xl.coef_doubles = coef_doubles; xl.ldx = sl.ldx; xl.nb_max = nb_max; xl.x_stride = sl.x_stride;
     xl.w_stride = (long long)((nb_max + 31) / 32 * 32) * sl.ldx;
     dl.w_stride = xl.w_stride;
+    xl.zmajor = dl.zmajor = ctx->split_solver ? 1 : 0;
     ctx->smem_flux = flux_smem(coef_doubles, sl.ldx, nb_max);
   }
   SelectPlan &sp = ctx->sp;
@@ -1503,6 +1507,27 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   if (G) {
     if (!g.slod) return fail(ctx, SLOD_ERR_STATE, "patch takes the LOD branch: no Gram matrix");
     CK(cudaMemcpy(G, ctx->d_G, sizeof(double) * g.Ncd * g.Ncd, cudaMemcpyDeviceToHost));
+  }
+  if (ctx->split_solver) {
+    // the split solver path keeps its coarse columns in z-major order (geom.h): back to the reference order
+    std::vector<int> zpos((size_t)g.Ncd);   // reference column -> internal column
+    for (int c = 0; c < g.Ncd; ++c) {
+      int k[3];
+      col_to_cell(ctx->P, g, c, k);
+      zpos[c] = zcell_to_col(g, k);
+    }
+    std::vector<double> tmp;
+    if (X) {
+      tmp.assign(X, X + (size_t)g.Ni * g.Ncd);
+      for (int r = 0; r < g.Ni; ++r)
+        for (int c = 0; c < g.Ncd; ++c) X[(size_t)r * g.Ncd + c] = tmp[(size_t)r * g.Ncd + zpos[c]];
+    }
+    for (double *Mx : {Minv, G})
+      if (Mx) {
+        tmp.assign(Mx, Mx + (size_t)g.Ncd * g.Ncd);
+        for (int r = 0; r < g.Ncd; ++r)
+          for (int c = 0; c < g.Ncd; ++c) Mx[(size_t)r * g.Ncd + c] = tmp[(size_t)zpos[r] * g.Ncd + zpos[c]];
+      }
   }
   return SLOD_OK;
 }

@@ -5,9 +5,10 @@
 //    per-patch table of the interior X rows of every coarse cell;
 //  * M^{-1}: blocked Gauss-Jordan (8 x 8 pivot blocks) with DMMA tile updates in shared memory (replaces
 //    FullMatrix::gauss_jordan, source/LOD.cc:553);
-//  * BD and the Gram matrix use FP64 mma.sync tiles: warp w owns the coarse-column tile [8w, 8w+8) of BD and two
-//    tile rows (w and NTILE-1-w, lower triangle only) of G, whose accumulators stay in registers while the
-//    boundary rows stream through shared memory in tiles of 32.
+//  * BD and the Gram matrix use FP64 mma.sync tiles: warp w owns the coarse-column tile [8w, 8w+8) of BD and one half
+//    of the lower-triangle tiles of the tile-row pair (r, NTILE-1-r), r = w mod NTILE/2 (every pair has NTILE + 1
+//    tiles, so the NTILE (NTILE + 1) / 2 tiles of the triangle are spread evenly and each is computed once); the
+//    accumulators stay in registers while the boundary rows stream through shared memory in tiles of 32.
 // Included by kernels.cu.
 #pragma once
 
@@ -60,7 +61,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       if (row < ncd && l < nloc) {
         const int comp = row % s;
         int k[3];
-        col_to_cell(cP, geo, row / s, k);
+        if (lay.zmajor) zcol_to_cell(geo, row / s, k);
+        else col_to_cell(cP, geo, row / s, k);
         int tt[3] = {l % npc, (l / npc) % npc, (cP.dim == 3) ? l / (npc * npc) : 0};
         int a[3] = {k[0] * cP.n + tt[0], k[1] * cP.n + tt[1], (cP.dim == 3) ? k[2] * cP.n + tt[2] : 0};
         if (node_class(cP, geo, a) == 0) {
@@ -210,9 +212,10 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
 
     // ---- BD tiles and Gram accumulation ----
-    double gacc[NTILE + 1][2];
+    constexpr int NGA = (NTILE + 2) / 2;   // Gram tiles per warp: half of the NTILE + 1 tiles of a tile-row pair
+    double gacc[NGA][2];
 #pragma unroll
-    for (int e = 0; e <= NTILE; ++e) gacc[e][0] = gacc[e][1] = 0.0;
+    for (int e = 0; e < NGA; ++e) gacc[e][0] = gacc[e][1] = 0.0;
     int nbd = 0;   // patch-boundary dofs (id 99): nodes on a patch side that is not part of the domain boundary
     {
       int cnt_all = 1, cnt_nob = 1;
@@ -223,7 +226,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       nbd = s * (cnt_all - cnt_nob);
     }
     const int ksteps = (ncd + 3) >> 2;
-    const int I1 = warp, I2 = NTILE - 1 - warp;
+    const int I1 = warp % (NTILE / 2), I2 = NTILE - 1 - I1;
+    const int e_base = (warp / (NTILE / 2)) * NGA;   // first entry of this warp in the pair's list of NTILE + 1 tiles
     // W = S_b X - P_b comes from k_patch_flux, zero padded to whole tiles; a thread moves 8 doubles of each tile
     // (NT * 8 = 32 * NC) and holds the next tile in registers while the tensor phases of the current one run.
     const double *Wp = Wbuf + (size_t)w * lay.w_stride;
@@ -263,10 +267,12 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         const double *rowp = sT + (4 * jj + t) * LDM + g;
         const double a1 = rowp[8 * I1], a2 = rowp[8 * I2];
 #pragma unroll
-        for (int e = 0; e <= NTILE; ++e) {
+        for (int el = 0; el < NGA; ++el) {
+          const int e = e_base + el;
+          if (e > NTILE) continue;
           const bool first = (e <= I1);
           const int J = first ? e : e - (I1 + 1);
-          dmma884(gacc[e][0], gacc[e][1], first ? a1 : a2, rowp[8 * J]);
+          dmma884(gacc[el][0], gacc[el][1], first ? a1 : a2, rowp[8 * J]);
         }
       }
       __syncthreads();   // the next tile overwrites sT
@@ -275,14 +281,16 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     {
       double *Go = G_out + (size_t)w * lay.m_stride;
 #pragma unroll
-      for (int e = 0; e <= NTILE; ++e) {
+      for (int el = 0; el < NGA; ++el) {
+        const int e = e_base + el;
+        if (e > NTILE) continue;
         const bool first = (e <= I1);
         const int I = first ? I1 : I2;
         const int J = first ? e : e - (I1 + 1);
         const int i = 8 * I + g, j = 8 * J + 2 * t;
         if (i < ncd) {
-          if (j < ncd) { Go[i * ncd + j] = gacc[e][0]; if (I != J) Go[j * ncd + i] = gacc[e][0]; }
-          if (j + 1 < ncd) { Go[i * ncd + j + 1] = gacc[e][1]; if (I != J) Go[(j + 1) * ncd + i] = gacc[e][1]; }
+          if (j < ncd) { Go[i * ncd + j] = gacc[el][0]; if (I != J) Go[j * ncd + i] = gacc[el][0]; }
+          if (j + 1 < ncd) { Go[i * ncd + j + 1] = gacc[el][1]; if (I != J) Go[(j + 1) * ncd + i] = gacc[el][1]; }
         }
       }
     }

@@ -171,7 +171,7 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
             if (rem != 0) wgt *= 2.0;
           }
         }
-        if (ok) W[(size_t)(t0 + rb) * lay.ldx + cell_to_col(cP, geo, kc) * s + dof % s] -= wgt;
+        if (ok) W[(size_t)(t0 + rb) * lay.ldx + (lay.zmajor ? zcell_to_col(geo, kc) : cell_to_col(cP, geo, kc)) * s + dof % s] -= wgt;
       }
     }
   }

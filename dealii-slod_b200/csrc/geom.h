@@ -129,6 +129,26 @@ SLOD_HD void col_to_cell(const Params &P, const Geom &g, int pos, int k[3]) {
   }
 }
 
+// Internal column order of the split solver path (3-D): the centre cell first (the selection addresses it as column 0,
+// like the reference order does), then the other cells sorted by their z coordinate (x outer, y inner inside a z
+// layer).  A coarse column is nonzero in P_i only on the fine nodes of its cell, so with this order the 8 columns a
+// warp of the triangular solver owns start at about the same row of the forward substitution and everything above is
+// skipped.  X, W, M^-1, G and c use it consistently between the solver and k_patch_finish; nothing the C ABI returns
+// is in this order (slod_debug_patch_stages permutes back).
+SLOD_HD int zcell_to_col(const Geom &g, const int k[3]) {
+  const int t = (k[2] * g.m[0] + k[0]) * g.m[1] + k[1];
+  const int tcz = (g.cc[2] * g.m[0] + g.cc[0]) * g.m[1] + g.cc[1];
+  return t == tcz ? 0 : (t < tcz ? t + 1 : t);
+}
+SLOD_HD void zcol_to_cell(const Geom &g, int pos, int k[3]) {
+  const int tcz = (g.cc[2] * g.m[0] + g.cc[0]) * g.m[1] + g.cc[1];
+  int t = (pos == 0) ? tcz : (pos <= tcz ? pos - 1 : pos);
+  k[1] = t % g.m[1];
+  t /= g.m[1];
+  k[0] = t % g.m[0];
+  k[2] = t / g.m[0];
+}
+
 SLOD_HD void node_coords(const Geom &g, int node, int a[3]) {
   a[0] = node % g.p[0];
   node /= g.p[0];

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "geom.h"
 #include "kernels.h"
@@ -973,12 +974,12 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
 constexpr int kSplitRB = 13, kFactorWarps = 8, kTriWarps = 16;
 size_t split_factor_smem(int coef_doubles, int nip_max) {
   const int R = 8 * kSplitRB, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * 64 + 64) +
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * 64 + 64 + 256) +
          sizeof(int) * ((size_t)nip_max + kSplitRB * (kSplitRB - 1) / 2 + 16 + 8);
 }
 size_t split_trisolve_smem(int nip_max) {
   return sizeof(double) * ((size_t)kTriStages * kSplitRB * 64) + 2 * kTriStages * sizeof(unsigned long long) +
-         sizeof(int) * ((size_t)nip_max + 8 * kTriWarps + 8);
+         sizeof(int) * ((size_t)nip_max + 8 * kTriWarps + kTriWarps + nip_max / 8 + 1 + 8 + 4);
 }
 long long split_rec_stride(int nip_max) { return (long long)(nip_max / 8) * kSplitRB * 64; }
 cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
@@ -987,6 +988,15 @@ cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const in
   SplitLayout lay{coef_doubles, nip_max, ldx, x_stride, split_rec_stride(nip_max)};
   cudaError_t e = cudaFuncSetAttribute(k_patch_factor<kSplitRB, kFactorWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // two CTAs per SM need nearly all of the 228 KB: ask for the largest shared-memory carve-out
+  e = cudaFuncSetAttribute(k_patch_factor<kSplitRB, kFactorWarps>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  if (getenv("SLOD_PRINT_OCC")) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_patch_factor<kSplitRB, kFactorWarps>, 32 * kFactorWarps, smem);
+    printf("k_patch_factor: %d CTAs/SM, %zu B dynamic shared memory\n", nb, smem);
+  }
   if (work_counter && (e = cudaMemsetAsync(work_counter, 0, sizeof(int), st)) != cudaSuccess) return e;
   k_patch_factor<kSplitRB, kFactorWarps><<<grid, 32 * kFactorWarps, smem, st>>>(ids, n_work, coef, Lrec, status, lay, work_counter);
   return cudaGetLastError();

@@ -27,6 +27,7 @@ struct DenseLayout {
   int ldx;
   long long x_stride;
   long long m_stride;  // ncd_max^2
+  int zmajor;          // coarse columns in the z-major order of the split solver (geom.h)
 };
 struct FluxLayout {
   int coef_doubles;
@@ -34,6 +35,7 @@ struct FluxLayout {
   int nb_max;
   long long x_stride;
   long long w_stride;  // doubles per patch in Wbuf: round_up(nb_max, 32) * ldx
+  int zmajor;          // coarse columns in the z-major order of the split solver (geom.h)
 };
 struct SelectLayout {
   int threads;

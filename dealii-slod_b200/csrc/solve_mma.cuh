@@ -74,6 +74,69 @@ __device__ __forceinline__ int chol8_inv(double v0, double v1, int lane, double 
   return bad;
 }
 
+// The same factorisation without any shuffle: every lane loads the lower triangle of the tile (broadcast reads of
+// shared memory, row stride ld) into registers and runs the whole LDL^T elimination redundantly -- all indices are
+// compile-time constants, the dependency chain per pivot is one MUFU reciprocal + Newton step, one multiplier and one
+// update, about half the latency of the shuffle version.  Lane l carries column (l & 7) of the transform M alongside;
+// lanes 0..7 write L^{-1} = D^{-1/2} M (row-major 8 x 8, zeros above the diagonal) to sLinv.  Returns nonzero if a
+// pivot was not positive.
+__device__ __forceinline__ int chol8_inv_reg(const double *T, int ld, int lane, double *sLinv) {
+  double a[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j + 1 <= i; j += 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(T + i * ld + j);
+      a[i][j] = v.x;
+      a[i][j + 1] = v.y;
+    }
+    if ((i & 1) == 0) a[i][i] = T[i * ld + i];
+  }
+  const int col = lane & 7;
+  double m[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = (i == col) ? 1.0 : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double dkk = a[k][k];
+    if (!(dkk > 0.0)) bad = 1;
+    rs[k] = dkk;          // scaled after the loop: the eight inverse square roots are independent of each other
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dkk));
+    const double er = fma(-dkk, rc, 1.0);
+    rc = fma(rc, fma(er, er, er), rc);
+    double mg[8];
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i) mg[i] = a[i][k] * rc;
+    // the next pivot first: it heads the dependency chain
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i)
+#pragma unroll
+      for (int j = k + 1; j <= i; ++j) a[i][j] = fma(-mg[i], a[j][k], a[i][j]);
+#pragma unroll
+    for (int i = k + 1; i < 8; ++i) m[i] = fma(-mg[i], m[k], m[i]);
+  }
+  // 1 / sqrt(d_k): MUFU seed (2^-22) + two Newton steps, branch free (the pivots are positive normal numbers), so the
+  // eight sequences interleave instead of running one after the other like eight calls of rsqrt() would
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rs[k]));
+    const double hx = 0.5 * rs[k];
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    rs[k] = fma(y, e, y);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sLinv[i * 8 + col] = (i >= col) ? m[i] * rs[i] : 0.0;
+  }
+  __syncwarp();
+  return bad;
+}
+
 constexpr int kSolveStages = 4;  // backward sweep: L panels staged this many steps ahead (they come back from HBM)
 
 struct SolveMmaLayout {

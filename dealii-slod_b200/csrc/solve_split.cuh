@@ -34,6 +34,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, int count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -55,7 +58,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
-constexpr int kTriStages = 8;   // ring depth of k_patch_trisolve (8 x 6.5 KB)
+// mma.sync.m16n8k8 f64: one instruction = four m8n8k4 (2048 flop), and far more latency tolerant -- a single warp per
+// scheduler sustains the tensor pipe with it (tools/dmma_operands.cu: 36.7 TFLOP/s against 31 / 23 with m8n8k4).
+// Fragments (g = lane >> 2, t = lane & 3): A a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); B b0 (t, g) b1 (t+4, g);
+// C c0,c1 (g, 2t..2t+1) c2,c3 (g+8, 2t..2t+1).
+__device__ __forceinline__ void dmma1688(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double a2,
+                                         double a3, double b0, double b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
+      : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+#ifdef SLOD_PHASE_CLOCKS
+#define PHS_DECL(wa, wb, wc) long long ph_acc[12] = {0}; long long ph_last = clock64(); const bool ph_on = (blockIdx.x == 0) && ((threadIdx.x & 31) == 0) && ((threadIdx.x >> 5) == (wa) || (threadIdx.x >> 5) == (wb) || (threadIdx.x >> 5) == (wc));
+#else
+#define PHS_DECL(wa, wb, wc)
+#endif
+
+constexpr int kTriStages = 12;  // ring depth of k_patch_trisolve (12 x 6.5 KB)
 
 struct SplitLayout {
   int coef_doubles;
@@ -68,32 +89,30 @@ struct SplitLayout {
 // position of element (r, c) of an 8 x 8 tile in A-fragment order
 __device__ __forceinline__ int frag_pos(int r, int c) { return 8 * r + 2 * (c & 3) + (c >> 2); }
 
-// Entry of the unconstrained stiffness matrix between interior node a and a + dl for the scalar 3-D problem with one
-// coefficient per sub-cell; the 8 x 8 reference matrix comes from shared memory (dynamic indexing of __constant__
-// memory serialises over the distinct addresses of a warp).
+// Entry of the unconstrained stiffness matrix between interior node a and a + dl (|dl_x| <= 1) for the scalar 3-D problem
+// with one coefficient per sub-cell: the sum over the (at most 8) sub-cells that contain both nodes of coefficient times
+// reference-matrix entry.  Fully unrolled over the 8 sub-cells around node a with independent loads, so that one entry
+// costs one shared-memory round trip, not eight; the 8 x 8 reference matrix comes from shared memory (dynamic indexing
+// of __constant__ memory serialises over the distinct addresses of a warp).  a is an INTERIOR node: all 8 sub-cells
+// around it exist.
 __device__ __forceinline__ double stiff_entry_3d(const Geom &g, const double *sCoef, const double *sK, int n,
                                                  const int a[3], const int dl[3]) {
-  int o0[3], o1[3];
-#pragma unroll
-  for (int x = 0; x < 3; ++x) {
-    const int msub = g.m[x] * n;
-    int lo_o = (dl[x] == 1) ? a[x] : a[x] - 1;
-    int hi_o = (dl[x] == -1) ? a[x] - 1 : a[x];
-    if (lo_o < 0) lo_o = 0;
-    if (hi_o > msub - 1) hi_o = msub - 1;
-    o0[x] = lo_o;
-    o1[x] = hi_o;
-  }
   const int msx = g.m[0] * n, msy = g.m[1] * n;
   double acc = 0.0;
-  for (int oz = o0[2]; oz <= o1[2]; ++oz)
-    for (int oy = o0[1]; oy <= o1[1]; ++oy)
-      for (int ox = o0[0]; ox <= o1[0]; ++ox) {
-        const int sc = (oz * msy + oy) * msx + ox;
-        const int la = (a[0] - ox) + 2 * (a[1] - oy) + 4 * (a[2] - oz);
-        const int lb = (a[0] + dl[0] - ox) + 2 * (a[1] + dl[1] - oy) + 4 * (a[2] + dl[2] - oz);
-        acc += sCoef[sc] * sK[la * 8 + lb];
-      }
+#pragma unroll
+  for (int oc = 0; oc < 8; ++oc) {
+    // sub-cell origin = a - (1,1,1) + bits of oc; node a is its local vertex la = 7 - oc (bit set <=> a is the upper node)
+    const int bx = oc & 1, by = (oc >> 1) & 1, bz = (oc >> 2) & 1;
+    // the other node a + dl is a vertex of the same sub-cell iff dl_x in {0, bx ? +1 : -1} per axis
+    const bool ok = (dl[0] == 0 || dl[0] == (bx ? 1 : -1)) && (dl[1] == 0 || dl[1] == (by ? 1 : -1)) &&
+                    (dl[2] == 0 || dl[2] == (bz ? 1 : -1));
+    const int ox = a[0] - 1 + bx, oy = a[1] - 1 + by, oz = a[2] - 1 + bz;
+    const int la = (1 - bx) + 2 * (1 - by) + 4 * (1 - bz);
+    const int lb = (1 - bx + dl[0]) + 2 * (1 - by + dl[1]) + 4 * (1 - bz + dl[2]);
+    const double c = sCoef[(oz * msy + oy) * msx + ox];
+    const double kv = sK[(la * 8 + lb) & 63];
+    acc += ok ? c * kv : 0.0;
+  }
   return acc;
 }
 
@@ -116,7 +135,8 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
   double *sLpT = sWf + R * LDWF;            // [8][LDP]  panel, k-major, slot rows
   double *sLinv = sLpT + 8 * LDP;           // [2][64]
   double *sK = sLinv + 2 * 64;              // [64] reference sub-cell matrix
-  int *sRowPk = (int *)(sK + 64);           // [nip_max] packed node coords / mask
+  double *sStage = sK + 64;                 // [2][128] lower-stencil entries of the block row entering the window next
+  int *sRowPk = (int *)(sStage + 256);      // [nip_max] packed node coords / mask
   int *sTileTab = sRowPk + lay.nip_max;     // [NTT] (offI | offJ << 8) of the trailing-update tiles
   int *sDOff = sTileTab + NTT;              // [16] dof offset of each lower stencil slot
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -173,22 +193,30 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
         *reinterpret_cast<double2 *>(sWf + (8 * sB + i) * LDWF + 2 * q) = make_double2(0.0, 0.0);
       }
     };
-    // the (at most 14) lower-stencil entries of each of the 8 rows of block `blk` into block row slot sB, computed
-    // on the fly from the sub-cell coefficients; item0 / nitem: the threads taking part
-    auto scatter_block_row = [&](int blk, int sB, int item0, int nitem) {
+    // the (at most 14) lower-stencil entries of each of the 8 rows of block `blk`, computed on the fly from the
+    // sub-cell coefficients: item = 8 * e + i is entry e of row i
+    auto stencil_item = [&](int blk, int item) -> double {
+      const int i = item & 7, e = item >> 3;
+      const int pk = sRowPk[8 * blk + i];
+      if (pk >= 0) return (e == 0) ? 1.0 : 0.0;       // padding row: identity (flagged through e == 0)
+      if (!((pk >> (16 + e)) & 1)) return 0.0;
+      const int a[3] = {pk & 31, (pk >> 5) & 31, (pk >> 10) & 31};
+      int dl[3];
+      lower_offset(e, dl);
+      return stiff_entry_3d(geo, sCoef, sK, n, a, dl);
+    };
+    // ... and their scatter into block row slot sB of the window; `val` holds the 112 entries of the block
+    auto scatter_block_row = [&](int blk, int sB, const double *val, int item0, int nitem) {
       for (int item = item0; item < 8 * (nlow + 1); item += nitem) {
         const int i = item & 7, e = item >> 3;
         const int r = 8 * blk + i;
         const int pk = sRowPk[r];
         if (pk < 0) {  // bit 31: a real dof row
           if (!((pk >> (16 + e)) & 1)) continue;
-          const int a[3] = {pk & 31, (pk >> 5) & 31, (pk >> 10) & 31};
-          int dl[3];
-          lower_offset(e, dl);
           const int c = r + sDOff[e];
           int sb = sB - (blk - (c >> 3));
           if (sb < 0) sb += RB;
-          sWf[(8 * sB + i) * LDWF + 8 * sb + (c & 7)] = stiff_entry_3d(geo, sCoef, sK, n, a, dl);
+          sWf[(8 * sB + i) * LDWF + 8 * sb + (c & 7)] = val[item];
         } else if (e == 0) {
           sWf[(8 * sB + i) * LDWF + 8 * sB + i] = 1.0;
         }
@@ -197,24 +225,37 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
 
     for (int b = 0; b < RB && b < NBLK; ++b) zero_block_row(b);
     __syncthreads();
-    for (int b = 0; b < RB && b < NBLK; ++b) scatter_block_row(b, b, tid, NT);
+    for (int b = 0; b < RB && b < NBLK; ++b) {   // the first RB block rows, through the staging buffer
+      if (tid < 8 * (nlow + 1)) sStage[tid] = stencil_item(b, tid);
+      __syncthreads();
+      scatter_block_row(b, b, sStage, tid, NT);
+      __syncthreads();
+    }
+    if (RB < NBLK && tid < 8 * (nlow + 1)) sStage[128 * (RB & 1) + tid] = stencil_item(RB, tid);   // block entering at step 0
     __syncthreads();
     int bad = 0;
-    if (warp == 0) {
-      const double v0 = sWf[g * LDWF + 2 * t], v1 = sWf[g * LDWF + 2 * t + 1];
-      bad |= chol8_inv(v0, v1, lane, sLinv);
-    }
+    if (warp == 0) bad |= chol8_inv_reg(sWf, LDWF, lane, sLinv);
     __syncthreads();
 
+    PHS_DECL(0, 3, NW - 1)
+    // One step = one full barrier.  Roles:
+    //   warp 0        the critical chain: panel tile (k+1, k), update and factorisation of the next diagonal tile --
+    //                 started at the top of the step, without waiting for the other panel tiles;
+    //   warp 4, ...   (the warps that share warp 0's scheduler, here and in the co-resident CTA) stay off the fp64
+    //                 pipe: record tile 0, window slide (zero + refill of the freed block row, next block staged);
+    //   other warps   panel tiles 2 .. nl, a named barrier among them and warp 0 (tile 1), trailing tiles.
+    constexpr int NTW = NW - NW / 4;          // panel / trailing warps
+    constexpr int NBAR = 32 * (NTW + 1);      // threads of the named barrier: those warps + warp 0
     for (int k = 0, kslot = 0; k < NBLK; ++k, kslot = (kslot + 1 == RB) ? 0 : kslot + 1) {
+      PH(0)
       const int cur = k & 1;
       const double *Linv = sLinv + cur * 64;
       int nl = NBLK - 1 - k;  // live panel blocks below the diagonal block
       if (nl > RB - 1) nl = RB - 1;
       double *Ls = rec + (size_t)k * LSTEP;
-      // ---- panel tiles  Lp_I = W[I, D] * Linv^T ----
+      const int ntile = nl * (nl + 1) / 2;
       const double binv0 = Linv[g * 8 + t], binv1 = Linv[g * 8 + 4 + t];  // B[k][n] = Linv[n][k]
-      for (int off = 1 + warp; off <= nl; off += NW) {
+      auto panel_tile = [&](int off) {   // Lp_I = W[I, D] * Linv^T, I = k + off
         int sI = kslot + off;
         if (sI >= RB) sI -= RB;
         const double *wt = sWf + (8 * sI + g) * LDWF + 8 * kslot;
@@ -226,17 +267,12 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
         double *dst = Ls + 64 * off;      // element (g, 2t) and (g, 2t + 1) in fragment order
         dst[frag_pos(g, 2 * t)] = p0;
         dst[frag_pos(g, 2 * t + 1)] = p1;
-      }
-      if (warp == NW - 1)   // tile 0 of the record: Linv in fragment order
-        *reinterpret_cast<double2 *>(Ls + 2 * lane) = make_double2(Linv[g * 8 + t], Linv[g * 8 + 4 + t]);
-      // block row kslot (block k) is dead: only its diagonal tile was still needed, by the factorisation of the
-      // previous step.  Clear it for block k + RB; the scatter follows after the barrier.
-      if (k + RB < NBLK) zero_block_row(kslot);
-      __syncthreads();
-      // ---- trailing update of the window, look-ahead factorisation of the next diagonal tile, window slide ----
-      const int ntile = nl * (nl + 1) / 2;
+      };
       if (warp == 0) {
-        if (ntile > 0) {
+        if (nl >= 1) {
+          panel_tile(1);
+          __syncwarp();
+          asm volatile("bar.arrive 1, %0;" ::"n"(NBAR) : "memory");   // tile 1 is in sLpT
           int sI = kslot + 1;
           if (sI >= RB) sI -= RB;
           double *ct = sWf + (8 * sI + g) * LDWF + 8 * sI + 2 * t;
@@ -245,13 +281,36 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
           dmma884(c.x, c.y, a0, -a0);
           dmma884(c.x, c.y, a1, -a1);
           *reinterpret_cast<double2 *>(ct) = c;
-          bad |= chol8_inv(c.x, c.y, lane, sLinv + (cur ^ 1) * 64);
+          __syncwarp();
+          PH(6)
+          bad |= chol8_inv_reg(sWf + (8 * sI) * LDWF + 8 * sI, LDWF, lane, sLinv + (cur ^ 1) * 64);
+          PH(7)
+        }
+      } else if ((warp & 3) == 0) {
+        if (warp == 4) {
+          // tile 0 of the record: Linv in fragment order
+          *reinterpret_cast<double2 *>(Ls + 2 * lane) = make_double2(Linv[g * 8 + t], Linv[g * 8 + 4 + t]);
+          // Block row kslot (block k) is dead: only its diagonal tile was still needed, by the factorisation of the
+          // previous step, and nothing of it is read in this step.  Clear it, refill it with block k + RB from the
+          // staging buffer, and compute the entries of block k + RB + 1 for the next step -- mostly integer work.
+          if (k + RB < NBLK) {
+            for (int item = lane; item < 32 * RB; item += 32) {
+              const int i = item & 7, q = item >> 3;
+              *reinterpret_cast<double2 *>(sWf + (8 * kslot + i) * LDWF + 2 * q) = make_double2(0.0, 0.0);
+            }
+            __syncwarp();
+            scatter_block_row(k + RB, kslot, sStage + 128 * ((k + RB) & 1), lane, 32);
+          }
+          if (k + RB + 1 < NBLK)
+            for (int item = lane; item < 8 * (nlow + 1); item += 32)
+              sStage[128 * ((k + RB + 1) & 1) + item] = stencil_item(k + RB + 1, item);
         }
       } else {
-        // the last warp first refills the freed block row (it is not touched by this step's updates)
-        if (warp == NW - 1 && k + RB < NBLK) scatter_block_row(k + RB, kslot, lane, 32);
-        constexpr int NTW = NW - 1;
-        const int wrank = warp - 1;
+        const int wrank = warp - 1 - (warp >> 2);  // 0 .. NTW-1
+        for (int off = 2 + wrank; off <= nl; off += NTW) panel_tile(off);
+        PH(1)
+        if (nl >= 1) asm volatile("bar.sync 1, %0;" ::"n"(NBAR) : "memory");
+        PH(3)
         for (int tt = 1 + wrank; tt < ntile; tt += 3 * NTW) {
           double *ct[3];
           double2 c[3];
@@ -280,8 +339,11 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
             if (tt + u * NTW < ntile) *reinterpret_cast<double2 *>(ct[u]) = c[u];
         }
       }
+      PH(4)
       __syncthreads();
+      PH(5)
     }
+    PH_PRINT("factor")
     if (bad && lane == 0) atomicOr(&status[pid], 1);
   }
 }
@@ -303,9 +365,17 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
   uint64_t *sEmpty = sFull + NSTG;                            // [NSTG]
   int *sRowPk = reinterpret_cast<int *>(sEmpty + NSTG);       // [nip_max] packed node coords of each interior dof
   int *sColCell = sRowPk + lay.nip_max;                       // [NC] packed cell coords of each coarse column (or -1)
+  int *sKstart = sColCell + NC;                               // [NW] first forward step of each warp
+  int *sNskip = sKstart + NW;                                 // [nip_max / 8 + 1] warps that sit out forward step k; last: backward
+  volatile uint32_t *sProgress = reinterpret_cast<volatile uint32_t *>(sNskip + lay.nip_max / 8 + 1);   // records issued so far
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int tpos = 8 * t + 2 * (g & 3) + (g >> 2);           // T^T fragment position, k-step 0 (+32 for k-step 1)
+  // Column group (8 columns) of this warp.  With the z-major column order the groups start their forward substitution
+  // at different rows (group 0-3 at row 0, 13-15 at 3/4 of the rows of a full patch); the map spreads early and late
+  // groups evenly over the four schedulers (warp mod 4).
+  const int grp = (NW == 16) ? (warp < 8 ? ((0x86543210u >> (4 * warp)) & 15) : ((0xCFED9BA7u >> (4 * (warp - 8))) & 15))
+                             : warp;
 
   if (tid == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -314,6 +384,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    *sProgress = 0;
   }
   __syncthreads();
   uint32_t rec_base = 0;   // records consumed so far by this CTA (ring position and barrier phases follow from it)
@@ -343,34 +414,72 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       int v = -1;
       if (col < ncd) {
         int kc[3];
-        col_to_cell(cP, geo, col, kc);
+        zcol_to_cell(geo, col, kc);   // z-major internal column order (geom.h)
         v = kc[0] | (kc[1] << 5) | (kc[2] << 10);
       }
       sColCell[col] = v;
     }
     __syncthreads();
-    const int mycc0 = sColCell[8 * warp + 2 * t], mycc1 = sColCell[8 * warp + 2 * t + 1];
+    const int mycc0 = sColCell[8 * grp + 2 * t], mycc1 = sColCell[8 * grp + 2 * t + 1];
     const int n = cP.n;
-    const double pw = cP.pw;
-    // right-hand-side tile (C layout) of block blk for this warp's columns: P_i entries from the tables
+    // Block rows in which the columns of this warp have right-hand-side entries: the fine nodes of a cell with z
+    // coordinate kz lie in the node planes n kz .. n kz + n.  Before the first of them the forward substitution of these
+    // columns is identically zero and is skipped; outside the range the incoming right-hand-side tiles are zero.
+    int kstart, kend;
+    {
+      int first = 1 << 30, last = -1;
+      const int cc = sColCell[8 * grp + (lane & 7)];
+      if (cc >= 0) {
+        const int kz = (cc >> 10) & 31;
+        int plo = n * kz, phi_ = n * kz + n;          // node planes of the cell
+        if (plo < 1) plo = 1;
+        if (phi_ > geo.p[2] - 2) phi_ = geo.p[2] - 2;  // interior planes only
+        first = (plo - 1) * geo.q[0] * geo.q[1];
+        last = phi_ * geo.q[0] * geo.q[1] - 1;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+      }
+      kstart = (last < 0) ? NBLK : first >> 3;       // last < 0: padding columns only, nothing to solve
+      kend = last >> 3;
+      if (lane == 0) sKstart[warp] = kstart;
+    }
+    __syncthreads();
+    // warps that do not take part in a step do not touch the ring: the producer arrives for them (below)
+    for (int k = tid; k <= NBLK; k += NT) {
+      int cnt = 0;
+      for (int w2 = 0; w2 < NW; ++w2) cnt += (k < NBLK) ? (sKstart[w2] > k) : (sKstart[w2] >= NBLK);
+      sNskip[k] = cnt;
+    }
+    __syncthreads();
+    const int pw_hi = __double2hiint(cP.pw), pw_lo = __double2loint(cP.pw);
+    // right-hand-side tile (C layout) of block blk for this warp's columns: P_i entries from the tables.  The weight
+    // pw * 2^(number of axes on which the node is interior to the cell) is put together from the exponent bits: no
+    // fp64 instruction competes with the tensor pipe.
     auto rhs_tile = [&](int blk, double &c0, double &c1) {
-      c0 = c1 = 0.0;
+      if (blk < kstart || blk > kend) {
+        c0 = c1 = 0.0;
+        return;
+      }
       const int pk = sRowPk[8 * blk + g];
-      if (pk >= 0) return;
+      int hi[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int cc = h ? mycc1 : mycc0;
-        if (cc < 0) continue;
-        double wgt = pw;
-        bool in = true;
+        bool in = (pk < 0) && (cc >= 0);
+        int cnt = 0;
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
           const int tt = ((pk >> (5 * x)) & 31) - n * ((cc >> (5 * x)) & 31);
-          if (tt < 0 || tt > n) in = false;
-          if (tt != 0 && tt != n) wgt *= 2.0;
+          in = in && (tt >= 0) && (tt <= n);
+          cnt += (tt != 0 && tt != n) ? 1 : 0;
         }
-        if (in) { if (h == 0) c0 = wgt; else c1 = wgt; }
+        hi[h] = in ? pw_hi + (cnt << 20) : 0;
       }
+      c0 = __hiloint2double(hi[0], hi[0] ? pw_lo : 0);
+      c1 = __hiloint2double(hi[1], hi[1] ? pw_lo : 0);
     };
 
     // ---- record stream of this patch: forward steps 0 .. NBLK-1, then backward steps NBLK-1 .. 0 ----
@@ -390,20 +499,33 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
         const uint32_t bytes = 8u * 64u * (1 + nl);
         mbar_expect_tx(sFull + slot, bytes);
         bulk_g2s(sRing + slot * LSTEP, rec + (size_t)k * LSTEP, bytes, sFull + slot);
+        const int nskip = sNskip[issued < NBLK ? k : NBLK];   // "empty" arrivals of the warps that skip this record
+        if (nskip > 0) mbar_arrive_n(sEmpty + slot, nskip);
         ++issued;
+        // No fence: once the wait on "empty" above has passed, the slot's "full" barrier is already in the phase of
+        // this record, so a consumer that sees the new count early still blocks until the bytes have landed.
+        *sProgress = rec_base + issued;
       }
     };
     if (tid == 0) top_up(NSTG - 1);
+    // Wait for record r in its ring slot.  The parity test of an mbarrier only tells the current phase from the one
+    // before it, and a warp that sat out the earlier uses of the slot may be several phases ahead of it: the record
+    // must have been ISSUED (then the slot's barrier is in the phase of this record, or past it) before the test.
+    auto wait_record = [&](uint32_t r, int slot) {
+      while ((int32_t)(*sProgress - r) <= 0) __nanosleep(100);
+      mbar_wait(sFull + slot, (r / NSTG) & 1);
+    };
 
     // =============================== forward substitution  L Y = P_i ===============================
     double cr[RBMAX][2];   // cr[off]: right-hand-side tile of block k + off (rotating register window)
 #pragma unroll
     for (int off = 0; off < RBMAX; ++off) {
       cr[off][0] = cr[off][1] = 0.0;
-      if (off < RB && off < NBLK) rhs_tile(off, cr[off][0], cr[off][1]);
+      if (off < RB && kstart + off < NBLK) rhs_tile(kstart + off, cr[off][0], cr[off][1]);
     }
-    for (int k = 0; k < NBLK; ++k) {
-      if (tid == 0) top_up(k + NSTG - 1);
+    PHS_DECL(0, 5, NW - 1)
+    for (int k = (warp == 0) ? 0 : kstart; k < NBLK; ++k) {   // warp 0 (the producer) owns column group 0: kstart = 0
+      PH(0)
       const uint32_t r = rec_base + k;
       const int slot = r % NSTG;
       int nl = NBLK - 1 - k;
@@ -412,7 +534,9 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       const double b0 = c_to_b(cr[0][0], cr[0][1], lane, 0), b1 = c_to_b(cr[0][0], cr[0][1], lane, 1);
       double n0 = 0.0, n1 = 0.0;
       if (k + RB < NBLK) rhs_tile(k + RB, n0, n1);
-      mbar_wait(sFull + slot, (r / NSTG) & 1);
+      PH(2)
+      wait_record(r, slot);
+      PH(3)
       const double2 *F = reinterpret_cast<const double2 *>(sRing + slot * LSTEP);
       double y0 = 0.0, y1 = 0.0;
       {
@@ -420,8 +544,10 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
         dmma884(y0, y1, li.x, b0);
         dmma884(y0, y1, li.y, b1);
       }
-      *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(y0, y1);
+      *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t) = make_double2(y0, y1);
       const double yb0 = -c_to_b(y0, y1, lane, 0), yb1 = -c_to_b(y0, y1, lane, 1);
+      // R_{k+off} -= Lp_off Y_k with m8n8k4: the short instruction keeps the wait of the NEXT step's dependent pair of
+      // Linv multiplications behind the other warps' tensor instructions short (m16n8k8 here: forward sweep 12 % slower)
 #pragma unroll
       for (int o4 = 1; o4 < RBMAX; o4 += 4) {
         double2 a[4];
@@ -435,8 +561,12 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
         for (int u = 0; u < 4; ++u)
           if (o4 + u < RBMAX && o4 + u <= nl) dmma884(cr[o4 + u][0], cr[o4 + u][1], a[u].y, yb1);
       }
+      // the producer refills the ring while the tensor pipe works through the instructions just issued
+      if (tid == 0) top_up(k + NSTG - 1);
+      PH(1)
       __syncwarp();
       if (lane == 0) mbar_arrive(sEmpty + slot);
+      PH(4)
       // the register window moves up by one block
 #pragma unroll
       for (int off = 0; off < RBMAX - 1; ++off) {
@@ -451,39 +581,53 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
     double xr[RBMAX][2];
 #pragma unroll
     for (int off = 0; off < RBMAX; ++off) xr[off][0] = xr[off][1] = 0.0;
-    auto y_tile = [&](int k) -> double2 {
-      return (k >= 0) ? *reinterpret_cast<const double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t)
-                      : make_double2(0.0, 0.0);
+    auto y_tile = [&](int k) -> double2 {   // Y_k of the forward sweep (zero, and never stored, before kstart)
+      return (k >= kstart) ? *reinterpret_cast<const double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t)
+                           : make_double2(0.0, 0.0);
     };
+    if (kstart >= NBLK && warp != 0) {
+      // padding columns only: X = 0 (finite values for the consumers), no arithmetic, no part in the ring
+      for (int k = 0; k < NBLK; ++k)
+        *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t) = make_double2(0.0, 0.0);
+      rec_base += (uint32_t)total;
+      continue;
+    }
+    // Two block rows per iteration (k and k - 1): X_{k+off} contributes to row k with panel tile off of step k and to
+    // row k - 1 with panel tile off + 1 of step k - 1 -- one m16n8k8 with the two transposed tiles stacked as A and the X
+    // block as B.  The one term of row k - 1 that needs X_k itself follows with m8n8k4.
     double2 ya = y_tile(NBLK - 1), yb = y_tile(NBLK - 2);
-    for (int k = NBLK - 1; k >= 0; --k) {
-      const int i = 2 * NBLK - 1 - k;   // record index
-      if (tid == 0) top_up(i + NSTG - 1);
+    for (int k = NBLK - 1; k >= 0; k -= 2) {
+      PH(5)
+      const bool two = (k >= 1);
+      const int i = 2 * NBLK - 1 - k;   // record index of step k; step k - 1 is record i + 1
       const uint32_t r = rec_base + i;
-      const int slot = r % NSTG;
+      const int slot = r % NSTG, slot2 = (r + 1) % NSTG;
       int nl = NBLK - 1 - k;
       if (nl > RB - 1) nl = RB - 1;
-      const double2 yn = y_tile(k - 2);
-      mbar_wait(sFull + slot, (r / NSTG) & 1);
-      const double *F = sRing + slot * LSTEP;
-      double c0 = ya.x, c1 = ya.y, e0 = 0.0, e1 = 0.0;   // two accumulation chains
+      int nl2 = NBLK - k;   // live panel tiles of step k - 1
+      if (nl2 > RB - 1) nl2 = RB - 1;
+      const double2 yna = y_tile(k - 2), ynb = y_tile(k - 3);
+      wait_record(r, slot);
+      if (two) wait_record(r + 1, slot2);
+      PH(7)
+      const double *F = sRing + slot * LSTEP, *F2 = sRing + slot2 * LSTEP;
+      double c[2][4] = {{ya.x, ya.y, yb.x, yb.y}, {0.0, 0.0, 0.0, 0.0}};   // two accumulation chains: rows k | k - 1
 #pragma unroll
-      for (int o2 = 1; o2 < RBMAX; o2 += 2) {
-        // A = Lp^T : A[m = g][kk = 4 j + t] = Lp[4 j + t][g]
-        double a0[2], a1[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (o2 + u < RBMAX && o2 + u <= nl) {
-            a0[u] = F[64 * (o2 + u) + tpos];
-            a1[u] = F[64 * (o2 + u) + 32 + tpos];
-          }
-        if (o2 <= nl) dmma884(c0, c1, a0[0], xr[o2][0]);
-        if (o2 + 1 < RBMAX && o2 + 1 <= nl) dmma884(e0, e1, a0[1], xr[o2 + 1][0]);
-        if (o2 <= nl) dmma884(c0, c1, a1[0], xr[o2][1]);
-        if (o2 + 1 < RBMAX && o2 + 1 <= nl) dmma884(e0, e1, a1[1], xr[o2 + 1][1]);
+      for (int off = 1; off < RBMAX; ++off) {
+        // A = [Lp_off(k)^T ; Lp_{off+1}(k-1)^T] : A[m][kk] = Lp[kk][m]
+        const bool lo_on = (off <= nl), hi_on = two && (off + 1 <= nl2) && (off + 1 < RBMAX);
+        if (lo_on || hi_on) {
+          const double a0 = lo_on ? F[64 * off + tpos] : 0.0, a2 = lo_on ? F[64 * off + 32 + tpos] : 0.0;
+          const double a1 = hi_on ? F2[64 * (off + 1 < RBMAX ? off + 1 : off) + tpos] : 0.0;
+          const double a3 = hi_on ? F2[64 * (off + 1 < RBMAX ? off + 1 : off) + 32 + tpos] : 0.0;
+          dmma1688(c[off & 1][0], c[off & 1][1], c[off & 1][2], c[off & 1][3], a0, a1, a2, a3, xr[off][0], xr[off][1]);
+        }
       }
-      c0 += e0;
-      c1 += e1;
+      if (tid == 0) top_up(i + NSTG - 3);   // slots of the pair before the previous one: warp 0 never waits for a straggler
+      PH(6)
+      const double c0 = c[0][0] + c[1][0], c1 = c[0][1] + c[1][1];
+      double p0 = c[0][2] + c[1][2], p1 = c[0][3] + c[1][3];
+      PH(8)
       // X_k = Linv_k^T T
       const double tb0 = c_to_b(c0, c1, lane, 0), tb1 = c_to_b(c0, c1, lane, 1);
       double x0 = 0.0, x1 = 0.0;
@@ -491,15 +635,34 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       dmma884(x0, x1, F[32 + tpos], tb1);
       __syncwarp();
       if (lane == 0) mbar_arrive(sEmpty + slot);
-      *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * warp + 2 * t) = make_double2(x0, x1);
+      *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t) = make_double2(x0, x1);
       const double nb0 = -c_to_b(x0, x1, lane, 0), nb1 = -c_to_b(x0, x1, lane, 1);
+      double mb0 = 0.0, mb1 = 0.0;
+      if (two) {
+        // row k - 1: the term with X_k (panel tile 1 of step k - 1), then X_{k-1} = Linv_{k-1}^T T
+        dmma884(p0, p1, F2[64 + tpos], nb0);
+        dmma884(p0, p1, F2[64 + 32 + tpos], nb1);
+        const double ub0 = c_to_b(p0, p1, lane, 0), ub1 = c_to_b(p0, p1, lane, 1);
+        double z0 = 0.0, z1 = 0.0;
+        dmma884(z0, z1, F2[tpos], ub0);
+        dmma884(z0, z1, F2[32 + tpos], ub1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sEmpty + slot2);
+        *reinterpret_cast<double2 *>(X + (size_t)(8 * (k - 1) + g) * lay.ldx + 8 * grp + 2 * t) = make_double2(z0, z1);
+        mb0 = -c_to_b(z0, z1, lane, 0);
+        mb1 = -c_to_b(z0, z1, lane, 1);
+      }
+      // the register window moves down by two block rows
 #pragma unroll
-      for (int off = RBMAX - 1; off >= 2; --off) { xr[off][0] = xr[off - 1][0]; xr[off][1] = xr[off - 1][1]; }
-      xr[1][0] = nb0;
-      xr[1][1] = nb1;
-      ya = yb;
-      yb = yn;
+      for (int off = RBMAX - 1; off >= 3; --off) { xr[off][0] = xr[off - 2][0]; xr[off][1] = xr[off - 2][1]; }
+      if (RBMAX > 2) { xr[2][0] = nb0; xr[2][1] = nb1; }
+      xr[1][0] = mb0;
+      xr[1][1] = mb1;
+      ya = yna;
+      yb = ynb;
+      PH(9)
     }
+    PH_PRINT("trisolve")
     rec_base += (uint32_t)total;
   }
 }
