@@ -300,18 +300,19 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     tk = np.zeros(8)
 
-    def run_basis(p0, p1):
-        ctx.compute_basis_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), stream)    # enqueues only
+    # One handle per process / GPU; the two all-gathers of the phase (A*phi before the coarse rows, the K row blocks
+    # after them) are NCCL calls INSIDE the library (slod_comm_init + slod_offline_distributed); torch.distributed only
+    # carries the 128-byte communicator id, the barrier and the max over ranks of the measured time.
+    if world > 1:
+        uid = torch.tensor(list(ctx.comm_unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8, device=dev)
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    p0, p1 = ctx.owned_range(rank, world)
 
-    def run_coarse(p0, p1):
-        ctx.assemble_coarse_device(p0, p1, phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), stream)
-
-    job = part.DistributedOffline(dist, rank, world, n, s, phi, aphi, K, run_basis, run_coarse,
-                                  synchronize=ctx.synchronize)
-    p0, p1 = job.p0, job.p1
-
-    def step():
-        job.step()            # ends with slod_synchronize: the step's status check, as a caller would do it
+    def step(gather_K=True):
+        ctx.offline_distributed(phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), gather_phi=False, gather_K=gather_K,
+                                stream=stream)
+        ctx.synchronize()     # the step's status check, as a caller would do it
         tk[:6] = ctx.timings()[:6]
         return tk.copy()
 
@@ -364,21 +365,19 @@ def main():
             path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_all_basis+slod_get_coarse_csr"
         else:
             h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
-            h_aphi = torch.empty_like(h_phi, pin_memory=True)
             h_K = torch.empty(((p1 - p0) * s, ellw), dtype=torch.float64, pin_memory=True)
 
             def e2e_step():
                 for f, tb in enumerate(tables):
                     ctx.set_coefficient(f, w["r"], tb)
-                job.step(gather_K=False)
+                step(gather_K=False)
                 h_phi.copy_(phi[p0:p1], non_blocking=True)
-                h_aphi.copy_(aphi[p0:p1], non_blocking=True)
                 h_K.copy_(K[p0 * s:p1 * s], non_blocking=True)
                 torch.cuda.synchronize()
                 return float(h_K[0, 0] + h_phi[0, 0, 0])
-            d2h = (p1 - p0) * s * (ellw + 2 * stride) * 8 * world
-            path = ("per rank: slod_set_coefficient+slod_compute_basis_device+all_gather(A phi)+"
-                    "slod_assemble_coarse_device+D2H of the rank's rows into pinned memory")
+            d2h = (p1 - p0) * s * (ellw + stride) * 8 * world
+            path = ("per rank: slod_set_coefficient + slod_offline_distributed (NCCL all-gather of A*phi inside the library) + "
+                    "D2H of the rank's own rows of phi and K into pinned memory (row-distributed result, as an MPI host holds it)")
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -422,13 +421,13 @@ def main():
     # ---- N > 1: the distributed result against a single-GPU recomputation on rank 0 (outside the timed region) ----
     multi_gpu_check = None
     if world > 1:
-        job.step()
+        step()
         torch.cuda.synchronize()
         if rank == 0:
             # patches of a sub-range that straddles the first partition boundary, recomputed by this rank alone into
             # fresh buffers; the coarse rows of the range need A*phi of their neighbours: take it from the gathered array
-            half = max(1, min(64, (job.ranges[0][1] - job.ranges[0][0]) // 2))
-            q0, q1 = job.ranges[0][1] - half, min(n, job.ranges[0][1] + half)
+            half = max(1, min(64, (p1 - p0) // 2))
+            q0, q1 = p1 - half, min(n, p1 + half)
             phi2 = torch.zeros_like(phi)
             aphi2 = torch.zeros_like(aphi)
             ctx.compute_basis_device(q0, q1, phi2.data_ptr(), aphi2.data_ptr(), stream)

@@ -27,14 +27,15 @@ EXPORTS = [
     "slod_get_patch_diagnostics", "slod_debug_patch_stages", "slod_get_timings", "slod_compute_basis_device",
     "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
     "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
-    "slod_fem_solve", "slod_fine_norms", "slod_synchronize", "slod_measure_fp64_peak",
+    "slod_fem_solve", "slod_fine_norms", "slod_synchronize", "slod_measure_fp64_peak", "slod_owned_range",
+    "slod_comm_unique_id", "slod_comm_init", "slod_offline_distributed",
 ]
 
 
 class SlodParams(C.Structure):
     _fields_ = [("dim", C.c_int), ("spacedim", C.c_int), ("n_global_refinements", C.c_int),
                 ("n_subdivisions", C.c_int), ("oversampling", C.c_int), ("stabilize", C.c_int),
-                ("problem", C.c_int), ("quirk_presaved", C.c_int), ("device", C.c_int)]
+                ("problem", C.c_int), ("quirk_presaved", C.c_int), ("device", C.c_int), ("n_gpus", C.c_int)]
 
 
 class SlodError(RuntimeError):
@@ -95,6 +96,10 @@ def load_library(path=None):
     lib.slod_alloc_host.argtypes = [C.c_size_t, P(vp)]
     lib.slod_free_host.argtypes = [vp]
     lib.slod_synchronize.argtypes = [vp]
+    lib.slod_owned_range.argtypes = [vp, C.c_int, C.c_int, P(i64), P(i64)]
+    lib.slod_comm_unique_id.argtypes = [vp]
+    lib.slod_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.slod_offline_distributed.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
     lib.slod_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
     _libs[path] = lib
     return lib
@@ -149,10 +154,10 @@ class SlodContext:
     """Thin object wrapper over the opaque ``slod_ctx`` handle."""
 
     def __init__(self, dim=2, spacedim=1, n_global_refinements=2, n_subdivisions=2, oversampling=1,
-                 stabilize=False, problem=PROBLEM_DIFFUSION, quirk_presaved=False, device=-1, lib=None):
+                 stabilize=False, problem=PROBLEM_DIFFUSION, quirk_presaved=False, device=-1, lib=None, n_gpus=0):
         self.lib = load_library(lib)
         self.par = SlodParams(dim, spacedim, n_global_refinements, n_subdivisions, oversampling,
-                              int(bool(stabilize)), problem, int(bool(quirk_presaved)), device)
+                              int(bool(stabilize)), problem, int(bool(quirk_presaved)), device, n_gpus)
         self.h = C.c_void_p()
         rc = self.lib.slod_create(C.byref(self.par), C.byref(self.h))
         if rc != SLOD_OK:
@@ -382,6 +387,28 @@ class SlodContext:
     def assemble_coarse_device(self, p0, p1, d_phi, d_aphi, d_K, stream=0):
         self._ck(self.lib.slod_assemble_coarse_device(self.h, p0, p1, C.c_void_p(d_phi), C.c_void_p(d_aphi),
                                                       C.c_void_p(d_K), C.c_void_p(stream)))
+
+    # -- one handle per GPU, NCCL inside the library ---------------------------------------------------------
+    def owned_range(self, rank, world):
+        b, e = C.c_int64(), C.c_int64()
+        self._ck(self.lib.slod_owned_range(self.h, rank, world, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def comm_unique_id(self):
+        """128 bytes of an ncclUniqueId (create on one rank, hand to the others)."""
+        buf = (C.c_char * 128)()
+        rc = self.lib.slod_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != SLOD_OK:
+            raise SlodError(rc, self.lib.slod_last_create_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.slod_comm_init(self.h, rank, world, C.cast(buf, C.c_void_p)))
+
+    def offline_distributed(self, d_phi, d_aphi, d_K, gather_phi=False, gather_K=True, stream=0):
+        self._ck(self.lib.slod_offline_distributed(self.h, C.c_void_p(d_phi), C.c_void_p(d_aphi), C.c_void_p(d_K),
+                                                   int(gather_phi), int(gather_K), C.c_void_p(stream)))
 
     def synchronize(self):
         """Wait for the device-buffer calls above; raises SlodError (SLOD_ERR_NUMERIC) if a patch reported a status."""

@@ -1,5 +1,7 @@
 // C ABI (include/slod.h) and host-side orchestration of the batched patch kernels.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: libnccl.so.2 is loaded with dlopen on the first multi-GPU call
 
 #include <algorithm>
 #include <array>
@@ -101,6 +103,10 @@ struct slod_ctx {
   size_t online_doubles = 0;
   double *d_val = nullptr;
   int64_t csr_nnz = 0;
+  // multi-GPU: (a) n_gpus > 1: this handle is rank 0 and owns one sub-handle per further device; (b) slod_comm_init
+  std::vector<slod_ctx *> subs;   // sub-handles of ranks 1 .. n_gpus-1 (owned)
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
 
 namespace {
@@ -120,6 +126,87 @@ int fail(const slod_ctx *c, int code, const std::string &msg) {
     if (e__ != cudaSuccess)                                                                        \
       return fail(ctx, SLOD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
   } while (0)
+
+
+// ---- NCCL, loaded on demand ---------------------------------------------------------------------------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) {
+      api.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return;
+    }
+    auto sym = [&](const char *n) {
+      void *p = dlsym(api.lib, n);
+      if (!p) api.err = std::string("libnccl misses ") + n;
+      return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  });
+  return &api;
+}
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      return fail(ctx, SLOD_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r__)); \
+  } while (0)
+
+void owned_range(int64_t n, int rank, int world, int64_t *b, int64_t *e) {
+  const int64_t base = n / world, rem = n % world;
+  *b = rank * base + std::min<int64_t>(rank, rem);
+  *e = *b + base + (rank < rem ? 1 : 0);
+}
+
+// In-place all-gather of the row blocks of `buf` ([n_patches * rows][row_doubles]): rank r contributes the rows of its
+// patch range.  Equal ranges: one ncclAllGather; ragged ranges: one broadcast per rank in a group (the blocks are
+// disjoint, nothing is reduced).
+int gather_blocks(slod_ctx *ctx, double *buf, size_t doubles_per_patch, cudaStream_t st) {
+  NcclApi *nc = nccl_api();
+  const int W = ctx->comm_world;
+  int64_t b, e;
+  owned_range(ctx->n_patches, ctx->comm_rank, W, &b, &e);
+  if (ctx->n_patches % W == 0) {
+    NK(nc->AllGather(buf + (size_t)b * doubles_per_patch, buf, (size_t)(e - b) * doubles_per_patch, ncclDouble, ctx->comm, st));
+  } else {
+    NK(nc->GroupStart());
+    for (int r = 0; r < W; ++r) {
+      int64_t rb, re;
+      owned_range(ctx->n_patches, r, W, &rb, &re);
+      if (re > rb)
+        NK(nc->Broadcast(buf + (size_t)rb * doubles_per_patch, buf + (size_t)rb * doubles_per_patch,
+                         (size_t)(re - rb) * doubles_per_patch, ncclDouble, r, ctx->comm, st));
+    }
+    NK(nc->GroupEnd());
+  }
+  return SLOD_OK;
+}
 
 int ipow(int b, int e) {
   int r = 1;
@@ -634,6 +721,84 @@ int ell_to_csr(const slod_ctx *ctx, const double *hK, int64_t *rowptr, int64_t *
   return SLOD_OK;
 }
 
+
+// ---- one handle, N devices (slod_params.n_gpus > 1): one host thread and one NCCL rank per device ----------------
+slod_ctx *rank_ctx(slod_ctx *ctx, int r) { return r == 0 ? ctx : ctx->subs[(size_t)r - 1]; }
+
+template <typename Fn>
+int for_each_rank(slod_ctx *ctx, Fn fn) {
+  const int N = 1 + (int)ctx->subs.size();
+  std::vector<int> rc((size_t)N, SLOD_OK);
+  std::vector<std::thread> th;
+  for (int r = 0; r < N; ++r)
+    th.emplace_back([&, r]() {
+      slod_ctx *c = rank_ctx(ctx, r);
+      if (cudaSetDevice(c->device) != cudaSuccess) {
+        rc[r] = fail(c, SLOD_ERR_CUDA, "cudaSetDevice failed");
+        return;
+      }
+      rc[r] = fn(c, r);
+    });
+  for (auto &t : th) t.join();
+  cudaSetDevice(ctx->device);
+  for (int r = 0; r < N; ++r)
+    if (rc[r] != SLOD_OK) {
+      if (r > 0) ctx->err = "device " + std::to_string(rank_ctx(ctx, r)->device) + ": " + rank_ctx(ctx, r)->err;
+      return rc[r];
+    }
+  return SLOD_OK;
+}
+
+int multi_basis(slod_ctx *ctx) {
+  const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax;
+  const size_t per_patch = (size_t)ctx->P.s * ctx->P.NfMax;
+  int rc = for_each_rank(ctx, [&](slod_ctx *c, int r) -> int {
+    slod_ctx *ctx = c;   // for the CK / NK macros
+    if (!c->d_phi) {
+      CK(cudaMalloc(&c->d_phi, sizeof(double) * n));
+      CK(cudaMalloc(&c->d_aphi, sizeof(double) * n));
+    }
+    int64_t b, e;
+    owned_range(c->n_patches, r, c->comm_world, &b, &e);
+    c->basis_done = c->coarse_done = false;
+    int rc2 = run_basis(c, b, e, c->d_phi, c->d_aphi, 0);
+    if (rc2) return rc2;
+    // every device ends up with A*phi (needed by the coarse-matrix rows of its range) and phi (rank 0 serves the
+    // host-buffer getters and the online phase) of every patch
+    rc2 = gather_blocks(c, c->d_aphi, per_patch, 0);
+    if (rc2) return rc2;
+    rc2 = gather_blocks(c, c->d_phi, per_patch, 0);
+    if (rc2) return rc2;
+    rc2 = wait_basis(c);
+    CK(cudaStreamSynchronize(0));
+    if (rc2) return rc2;
+    c->basis_done = true;
+    return SLOD_OK;
+  });
+  for (int k = 0; k < 8; ++k)
+    for (slod_ctx *c : ctx->subs) ctx->tm.ms[k] = std::max(ctx->tm.ms[k], c->tm.ms[k]);
+  return rc;
+}
+
+int multi_coarse(slod_ctx *ctx) {
+  const size_t n = (size_t)ctx->n_patches * ctx->P.s * ctx->P.ell_width;
+  int rc = for_each_rank(ctx, [&](slod_ctx *c, int r) -> int {
+    slod_ctx *ctx = c;
+    if (!c->d_Kell) CK(cudaMalloc(&c->d_Kell, sizeof(double) * n));
+    int64_t b, e;
+    owned_range(c->n_patches, r, c->comm_world, &b, &e);
+    int rc2 = run_coarse(c, b, e, c->d_phi, c->d_aphi, c->d_Kell, 0, false);
+    if (rc2) return rc2;
+    rc2 = gather_blocks(c, c->d_Kell, (size_t)c->P.s * c->P.ell_width, 0);   // disjoint row blocks, everywhere
+    if (rc2) return rc2;
+    rc2 = finish_coarse_timing(c);
+    CK(cudaStreamSynchronize(0));
+    return rc2;
+  });
+  for (slod_ctx *c : ctx->subs) ctx->tm.ms[4] = std::max(ctx->tm.ms[4], c->tm.ms[4]);
+  return rc;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -664,6 +829,8 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   if (par->n_subdivisions < 1 || (par->n_subdivisions & (par->n_subdivisions - 1)))
     return bad(SLOD_ERR_INVALID, "n_subdivisions must be a power of two (include/Diffusion.h:76-80)");
   if (par->oversampling < 0) return bad(SLOD_ERR_INVALID, "oversampling < 0");
+  if (par->n_gpus < 0) return bad(SLOD_ERR_INVALID, "n_gpus < 0");
+  if (par->n_gpus > 1 && par->device == SLOD_DEVICE_NONE) return bad(SLOD_ERR_INVALID, "n_gpus > 1 on a maps-only handle");
 
   // device == SLOD_DEVICE_NONE: integer maps only (patch lists, DoF maps, CSR pattern); every compute
   // entry point of such a handle fails with SLOD_ERR_CUDA -- there is no CPU fallback.
@@ -677,8 +844,11 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       return bad(SLOD_ERR_CUDA, "no CUDA device: libslod_b200 has no CPU fallback");
+    if (dev < 0 && par->n_gpus > 1) dev = 0;
     if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return bad(SLOD_ERR_CUDA, "cudaGetDevice failed");
     if (dev >= ndev) return bad(SLOD_ERR_INVALID, "device ordinal out of range");
+    if (par->n_gpus > 1 && dev + par->n_gpus > ndev)
+      return bad(SLOD_ERR_INVALID, "n_gpus: not enough CUDA devices after `device`");
     if (cudaSetDevice(dev) != cudaSuccess) return bad(SLOD_ERR_CUDA, "cudaSetDevice failed");
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
       return bad(SLOD_ERR_CUDA, "cudaGetDeviceProperties failed");
@@ -901,6 +1071,44 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   for (auto &ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_bad("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev_split)) != cudaSuccess) return cuda_bad("cudaEventCreate", e);
+  if (par->n_gpus > 1) {
+    // one sub-handle per further device, one NCCL communicator over all of them
+    NcclApi *nc = nccl_api();
+    if (!nc->err.empty()) {
+      g_create_error = nc->err;
+      slod_destroy(ctx);
+      return SLOD_ERR_CUDA;
+    }
+    const int N = par->n_gpus;
+    slod_params sp1 = *par;
+    sp1.n_gpus = 1;
+    for (int r = 1; r < N; ++r) {
+      sp1.device = dev + r;
+      slod_ctx *sub = nullptr;
+      const int rc = slod_create(&sp1, &sub);
+      if (rc != SLOD_OK) {
+        slod_destroy(ctx);
+        return rc;
+      }
+      ctx->subs.push_back(sub);
+    }
+    std::vector<int> devs((size_t)N);
+    for (int r = 0; r < N; ++r) devs[r] = dev + r;
+    std::vector<ncclComm_t> comms((size_t)N);
+    const ncclResult_t nr = nc->CommInitAll(comms.data(), N, devs.data());
+    if (nr != ncclSuccess) {
+      g_create_error = std::string("ncclCommInitAll: ") + nc->GetErrorString(nr);
+      slod_destroy(ctx);
+      return SLOD_ERR_CUDA;
+    }
+    for (int r = 0; r < N; ++r) {
+      slod_ctx *c = rank_ctx(ctx, r);
+      c->comm = comms[r];
+      c->comm_rank = r;
+      c->comm_world = N;
+    }
+    cudaSetDevice(dev);
+  }
   *out = ctx;
   return SLOD_OK;
 }
@@ -911,8 +1119,11 @@ void slod_destroy(slod_ctx *ctx) {
     delete ctx;
     return;
   }
+  for (slod_ctx *sub : ctx->subs) slod_destroy(sub);
+  ctx->subs.clear();
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();   // slod_assemble_coarse only enqueues
+  if (ctx->comm) nccl_api()->CommDestroy(ctx->comm);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   free_dev(ctx);
   for (auto &ev : ctx->ev)
@@ -938,6 +1149,10 @@ int slod_set_coefficient(slod_ctx *ctx, int field, int eta_refinement, const dou
   ctx->coef_set[field] = true;
   ctx->coef_dirty = true;
   ctx->basis_done = ctx->coarse_done = false;
+  for (slod_ctx *sub : ctx->subs) {
+    const int rc = slod_set_coefficient(sub, field, eta_refinement, cellwise, n);
+    if (rc) return fail(ctx, rc, sub->err);
+  }
   return SLOD_OK;
 }
 
@@ -1078,6 +1293,7 @@ int slod_launch_count(const slod_ctx *ctx, int64_t *n) {
 int slod_compute_basis_device(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_aphi, void *stream) {
   if (!ctx || !d_phi || !d_aphi) return SLOD_ERR_INVALID;
   NEED_DEVICE();
+  if (!ctx->subs.empty()) return fail(ctx, SLOD_ERR_UNSUPPORTED, "device-buffer entry points need a single-device handle (n_gpus <= 1)");
   CK(cudaSetDevice(ctx->device));
   return run_basis(ctx, p0, p1, d_phi, d_aphi, (cudaStream_t)stream);
 }
@@ -1086,6 +1302,7 @@ int slod_assemble_coarse_device(slod_ctx *ctx, int64_t p0, int64_t p1, const dou
                                 double *d_K, void *stream) {
   if (!ctx || !d_phi || !d_aphi || !d_K) return SLOD_ERR_INVALID;
   NEED_DEVICE();
+  if (!ctx->subs.empty()) return fail(ctx, SLOD_ERR_UNSUPPORTED, "device-buffer entry points need a single-device handle (n_gpus <= 1)");
   CK(cudaSetDevice(ctx->device));
   return run_coarse(ctx, p0, p1, d_phi, d_aphi, d_K, (cudaStream_t)stream, false);   // enqueue only, see slod_synchronize
 }
@@ -1100,12 +1317,75 @@ int slod_compute_basis(slod_ctx *ctx) {
     CK(cudaMalloc(&ctx->d_aphi, sizeof(double) * n));
   }
   ctx->basis_done = ctx->coarse_done = false;
+  if (!ctx->subs.empty()) return multi_basis(ctx);
   int rc = run_basis(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, 0);
   if (rc) return rc;
   rc = wait_basis(ctx);
   if (rc) return rc;
   ctx->basis_done = true;
   return SLOD_OK;
+}
+
+int slod_owned_range(const slod_ctx *ctx, int rank, int world, int64_t *b, int64_t *e) {
+  if (!ctx || !b || !e) return SLOD_ERR_INVALID;
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SLOD_ERR_INVALID, "rank out of range");
+  owned_range(ctx->n_patches, rank, world, b, e);
+  return SLOD_OK;
+}
+
+int slod_comm_unique_id(void *id128) {
+  if (!id128) return SLOD_ERR_INVALID;
+  NcclApi *nc = nccl_api();
+  if (!nc->err.empty()) {
+    g_create_error = nc->err;
+    return SLOD_ERR_CUDA;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (nc->GetUniqueId(&id) != ncclSuccess) return SLOD_ERR_CUDA;
+  std::memcpy(id128, &id, sizeof id);
+  return SLOD_OK;
+}
+
+int slod_comm_init(slod_ctx *ctx, int rank, int world, const void *id128) {
+  if (!ctx || !id128) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->subs.empty()) return fail(ctx, SLOD_ERR_STATE, "handle already drives several devices (n_gpus > 1)");
+  if (ctx->comm) return fail(ctx, SLOD_ERR_STATE, "communicator already initialised");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SLOD_ERR_INVALID, "rank out of range");
+  NcclApi *nc = nccl_api();
+  if (!nc->err.empty()) return fail(ctx, SLOD_ERR_CUDA, nc->err);
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  NK(nc->CommInitRank(&ctx->comm, world, id, rank));
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return SLOD_OK;
+}
+
+int slod_offline_distributed(slod_ctx *ctx, double *d_phi, double *d_aphi, double *d_K, int gather_phi, int gather_K,
+                             void *stream) {
+  if (!ctx || !d_phi || !d_aphi || !d_K) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->subs.empty()) return fail(ctx, SLOD_ERR_UNSUPPORTED, "use slod_compute_basis / slod_assemble_coarse on an n_gpus > 1 handle");
+  if (ctx->comm_world > 1 && !ctx->comm) return fail(ctx, SLOD_ERR_STATE, "slod_comm_init has not run");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t b, e;
+  owned_range(ctx->n_patches, ctx->comm_rank, ctx->comm_world, &b, &e);
+  const size_t per_patch = (size_t)ctx->P.s * ctx->P.NfMax;
+  int rc = run_basis(ctx, b, e, d_phi, d_aphi, st);
+  if (rc) return rc;
+  if (ctx->comm_world > 1) {
+    rc = gather_blocks(ctx, d_aphi, per_patch, st);
+    if (rc) return rc;
+    if (gather_phi && (rc = gather_blocks(ctx, d_phi, per_patch, st))) return rc;
+  }
+  rc = run_coarse(ctx, b, e, d_phi, d_aphi, d_K, st, false);
+  if (rc) return rc;
+  if (ctx->comm_world > 1 && gather_K) rc = gather_blocks(ctx, d_K, (size_t)ctx->P.s * ctx->P.ell_width, st);
+  return rc;
 }
 
 int slod_synchronize(slod_ctx *ctx) {
@@ -1191,7 +1471,10 @@ int slod_assemble_coarse(slod_ctx *ctx) {
   // the matrix is stream ordered behind them, and an execution error surfaces at that consumer's synchronisation.
   int rc = build_csr_cache(ctx);   // first call only: host-side integer geometry, before the kernels are in flight
   if (rc) return rc;
-  rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0, false);
+  if (!ctx->subs.empty())
+    rc = multi_coarse(ctx);   // row blocks on N devices + NCCL all-gather; the matrix is complete on return
+  else
+    rc = run_coarse(ctx, 0, ctx->n_patches, ctx->d_phi, ctx->d_aphi, ctx->d_Kell, 0, false);
   if (rc) return rc;
   CK(launch_gather(0, ctx->d_Kell, ctx->d_perm, ctx->d_val, ctx->csr_nnz));   // compact block-ELL -> CSR values
   ctx->launches += 1;

@@ -184,6 +184,7 @@ public:
     prm.declare(P + "/Solver/Fine solver control", "Tolerance", "1e-10");
     prm.declare(P + "/Solver/Fine solver control", "Reduction", "1e-2");
     prm.declare(P + "/B200", "Device", "-1");              // [+] CUDA device ordinal, -1 = current
+    prm.declare(P + "/B200", "Number of GPUs", "1");       // [+] devices driven by the one handle (NCCL inside the library)
     prm.declare(P + "/B200", "Write coarse matrix", "true");
   }
   // ParameterAcceptor::initialize(prm_file): parse, or write a template and keep the defaults
@@ -212,6 +213,7 @@ public:
     fine_tolerance = prm.get_double(P + "/Solver/Fine solver control", "Tolerance");
     fine_reduction = prm.get_double(P + "/Solver/Fine solver control", "Reduction");
     device = (int)prm.get_integer(P + "/B200", "Device");
+    n_gpus = (int)nonneg(prm.get_integer(P + "/B200", "Number of GPUs"), "Number of GPUs");
     write_coarse_matrix = prm.get_bool(P + "/B200", "Write coarse matrix");
     (void)rhs_constants();   // refuse what this host cannot evaluate before any work is done
   }
@@ -234,6 +236,7 @@ public:
   unsigned int fine_max_steps = 100;
   double fine_tolerance = 1e-10, fine_reduction = 1e-2;
   int device = -1;
+  int n_gpus = 1;
   bool write_coarse_matrix = true;
 
   // the constant value of every component of the right-hand side; anything but numbers is refused
@@ -426,6 +429,7 @@ protected:
     p.problem = (spacedim == 1) ? SLOD_PROBLEM_DIFFUSION : SLOD_PROBLEM_ELASTICITY;
     p.quirk_presaved = par.constant_coefficients ? 1 : 0;  // source/LOD.cc:354-362
     p.device = par.device;
+    p.n_gpus = par.n_gpus;   // locally_owned_patches over the devices of this process (source/LOD.cc:116-118)
     check(slod_create(&p, &slod), "slod_create");
     int64_t n = 0;
     check(slod_patch_count(slod, &n), "slod_patch_count");

@@ -19,8 +19,12 @@
  *  - host-buffer calls return when their results are complete, with one exception: slod_assemble_coarse only enqueues
  *    (see there).  The device-buffer entry points (slod_*_device) only enqueue on the caller's stream;
  *    slod_synchronize() is their synchronisation point and reports numerical failures of the enqueued patches.
- *  - one handle drives ONE CUDA device (one process per GPU; the collective between ranks is done
- *    by the caller on the device buffers, see slod_*_device entry points).
+ *  - multi-GPU, two ways, both with NCCL inside the library (libnccl.so.2 is loaded on first use, a single-GPU handle
+ *    never needs it): (a) slod_params.n_gpus = N -- one handle, one process, N devices; slod_compute_basis and
+ *    slod_assemble_coarse split the patches over the devices and combine the results over NVLink, every other call
+ *    behaves as on one device; (b) one process and one handle per GPU (MPI / torchrun style): slod_comm_init joins the
+ *    handles into one NCCL communicator and slod_offline_distributed runs the phase with its two all-gathers.
+ *    The slod_*_device entry points remain for callers that do their own exchange.
  *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
  *  - a handle is thread-compatible, not thread-safe; the kernels read their parameters from one __constant__ block
  *    per process, so compute calls of DIFFERENT handles of one process must not overlap in time either (sequential
@@ -70,6 +74,10 @@ typedef struct {
   int problem;              /* SLOD_PROBLEM_*                                                     */
   int quirk_presaved;       /* reproduce source/LOD.cc:354-362 ("Constant problem coefficients") */
   int device;               /* CUDA device ordinal, SLOD_DEVICE_CURRENT or SLOD_DEVICE_NONE        */
+  int n_gpus;               /* 0 or 1: the handle drives `device` alone.  N > 1: ONE handle drives the N devices
+                               device .. device + N - 1 of this process (SLOD_DEVICE_CURRENT counts as 0): the patches
+                               are split into contiguous even ranges (the reference's locally_owned_patches,
+                               source/LOD.cc:116-118), one host thread and one NCCL rank per device inside the library */
 } slod_params;
 
 /* life cycle ------------------------------------------------------------------------------------*/
@@ -189,6 +197,22 @@ int slod_assemble_coarse_device(slod_ctx *ctx, int64_t patch_begin, int64_t patc
  * (A_ii or M not positive definite, eigen-solver not converged) -- the same mapping slod_compute_basis does. */
 int slod_synchronize(slod_ctx *ctx);
 int slod_ell_width(const slod_ctx *ctx, int64_t *width);
+
+/* ---- one handle per GPU, NCCL inside the library (multi-process multi-GPU) ---------------------------------------*/
+/* [begin, end) of the patch ids owned by `rank` of `world`: create_evenly_distributed_partitioning
+ * (source/LOD.cc:116-118) -- contiguous blocks, the first n % world ranks hold one more. */
+int slod_owned_range(const slod_ctx *ctx, int rank, int world, int64_t *patch_begin, int64_t *patch_end);
+/* 128 bytes of an ncclUniqueId, to be created by one rank and handed to the others by the caller (MPI_Bcast,
+ * torch.distributed.broadcast, a file, ...). */
+int slod_comm_unique_id(void *id128);
+/* Join this handle (its device) into a communicator of `world` ranks. */
+int slod_comm_init(slod_ctx *ctx, int rank, int world, const void *id128);
+/* The offline phase of this rank on device arrays of the full layout ([n_patches][spacedim][stride] and
+ * [n_patches * spacedim][ell_width], as in the *_device calls): basis of the owned range, all-gather of A*phi (and of
+ * phi when gather_phi != 0), coarse-matrix rows of the owned range, all-gather of the row blocks when gather_K != 0.
+ * Everything is enqueued on `stream`; slod_synchronize() is the synchronisation point. */
+int slod_offline_distributed(slod_ctx *ctx, double *d_phi, double *d_A_phi, double *d_K, int gather_phi, int gather_K,
+                             void *stream);
 /* convert a host copy of the block-ELL matrix into CSR (same contract as slod_get_coarse_csr) */
 int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,
                     int64_t *n_rows, int64_t *nnz);

@@ -118,3 +118,14 @@ def test_csr_pattern_matches_sparse_product(lib, dim, s, ref, ell):
             D = [cq[a] - cp[a] + w for a in range(dim)]
             slot = D[0] + ww * D[1] + (ww * ww * D[2] if dim == 3 else 0)
             assert val[k] == hK[r, slot * s + e]
+
+
+def test_owned_range_is_the_reference_partition(lib):
+    """slod_owned_range = create_evenly_distributed_partitioning (source/LOD.cc:116-118), as partition.py restates it."""
+    ctx = pkg.SlodContext(dim=2, n_global_refinements=3, device=-2)
+    part = importlib.import_module("dealii-slod_b200.partition")
+    for world in (1, 2, 3, 5, 8):
+        for r in range(world):
+            assert ctx.owned_range(r, world) == part.owned_range(ctx.n_patches, r, world)
+    with pytest.raises(pkg.SlodError):
+        ctx.owned_range(3, 3)
