@@ -258,6 +258,11 @@ def config_of(w, wname):
 
 
 # ------------------------------------------------------------------------------------------------------
+def _dbg(*a):
+    if os.environ.get("SLOD_BENCH_DEBUG"):
+        print("[bench]", os.environ.get("RANK", "0"), *a, file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,9 +327,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    _dbg("warm-up")
     for _ in range(args.warmup):
         step()
     barrier()
+    _dbg("timed region")
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ksum = np.zeros(8)
@@ -335,6 +342,7 @@ def main():
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
+    _dbg("timed done", ms_total)
     launches = ctx.launch_count - l0
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -420,6 +428,7 @@ def main():
 
     # ---- N > 1: the distributed result against a single-GPU recomputation on rank 0 (outside the timed region) ----
     multi_gpu_check = None
+    _dbg("e2e done")
     if world > 1:
         step()
         torch.cuda.synchronize()
@@ -445,8 +454,16 @@ def main():
             if not (same_phi and same_aphi and same_K):
                 raise SystemExit(f"multi-GPU result differs from the single-GPU recomputation: {multi_gpu_check}")
             del phi2, aphi2, K2
+        # The other ranks wait on the HOST (the rendezvous store), not in an NCCL barrier: a collective kernel spinning
+        # on their GPUs while rank 0 allocates memory (cudaMalloc synchronises with peer-mapped devices) deadlocks.
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("slod_check_done", "1")
+        else:
+            store.wait(["slod_check_done"])
         barrier()
 
+    _dbg("check done")
     if rank == 0:
         fm = flop_model(w)
         names = ["patch_solve", "patch_dense", "patch_select", "patch_finish"]

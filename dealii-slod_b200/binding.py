@@ -28,7 +28,8 @@ EXPORTS = [
     "slod_assemble_coarse_device", "slod_ell_width", "slod_ell_to_csr", "slod_launch_count", "slod_alloc_host",
     "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
     "slod_fem_solve", "slod_fine_norms", "slod_synchronize", "slod_measure_fp64_peak", "slod_owned_range",
-    "slod_comm_unique_id", "slod_comm_init", "slod_offline_distributed",
+    "slod_comm_unique_id", "slod_comm_init", "slod_offline_distributed", "slod_save_state", "slod_load_state",
+    "slod_fine_norms_reference",
 ]
 
 
@@ -96,6 +97,9 @@ def load_library(path=None):
     lib.slod_alloc_host.argtypes = [C.c_size_t, P(vp)]
     lib.slod_free_host.argtypes = [vp]
     lib.slod_synchronize.argtypes = [vp]
+    lib.slod_fine_norms_reference.argtypes = [vp, P(dbl), P(dbl), P(dbl), P(dbl)]
+    lib.slod_save_state.argtypes = [vp, C.c_char_p]
+    lib.slod_load_state.argtypes = [vp, C.c_char_p]
     lib.slod_owned_range.argtypes = [vp, C.c_int, C.c_int, P(i64), P(i64)]
     lib.slod_comm_unique_id.argtypes = [vp]
     lib.slod_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -348,6 +352,15 @@ class SlodContext:
         self._ck(self.lib.slod_fine_norms(self.h, _dp(v), C.byref(l2), C.byref(h1), C.byref(en)))
         return l2.value, h1.value, en.value
 
+    def fine_norms_reference(self, v_fine):
+        """(L2_norm, Linfty_norm, H1_norm) with the reference's quadrature (ParsedConvergenceTable::difference)."""
+        v = np.ascontiguousarray(v_fine, dtype=np.float64).ravel()
+        if v.size != self.n_fine:
+            raise ValueError(f"fine vector has {v.size} entries, expected {self.n_fine}")
+        l2, li, h1 = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.slod_fine_norms_reference(self.h, _dp(v), C.byref(l2), C.byref(li), C.byref(h1)))
+        return l2.value, li.value, h1.value
+
     def diagnostics(self, patch, comp=0):
         out = np.empty(8)
         self._ck(self.lib.slod_get_patch_diagnostics(self.h, patch, comp, _dp(out)))
@@ -409,6 +422,13 @@ class SlodContext:
     def offline_distributed(self, d_phi, d_aphi, d_K, gather_phi=False, gather_K=True, stream=0):
         self._ck(self.lib.slod_offline_distributed(self.h, C.c_void_p(d_phi), C.c_void_p(d_aphi), C.c_void_p(d_K),
                                                    int(gather_phi), int(gather_K), C.c_void_p(stream)))
+
+    def save_state(self, path):
+        """Checkpoint of the offline phase (basis + coarse matrix) to one binary file."""
+        self._ck(self.lib.slod_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path):
+        self._ck(self.lib.slod_load_state(self.h, os.fsencode(path)))
 
     def synchronize(self):
         """Wait for the device-buffer calls above; raises SlodError (SLOD_ERR_NUMERIC) if a patch reported a status."""

@@ -1717,6 +1717,164 @@ int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_
   return SLOD_OK;
 }
 
+// Gauss-Legendre rule on [0, 1] (Newton iteration on the Legendre polynomial)
+static void gauss_rule(int nq, std::vector<double> &x, std::vector<double> &w) {
+  x.resize(nq);
+  w.resize(nq);
+  for (int i = 0; i < nq; ++i) {
+    double z = std::cos(M_PI * (i + 0.75) / (nq + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 1; j <= nq; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+      }
+      pp = nq * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (std::fabs(dz) < 1e-15) break;
+    }
+    x[nq - 1 - i] = 0.5 * (1.0 + z);
+    w[nq - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+int slod_fine_norms_reference(slod_ctx *ctx, const double *v_fine, double *l2, double *linfty, double *h1) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!v_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  CK(upload_params(ctx->P));
+  int64_t n_fine = 0;
+  slod_fine_size(ctx, &n_fine);
+  const int nq = 2 * (ctx->P.n + 1);   // QGauss((fe.degree + 1) * 2), degree of FE_Q_iso_Q1(n) = n
+  std::vector<double> gx, gw;
+  gauss_rule(nq, gx, gw);
+  int nb = 0;
+  launch_fine_norms_reference(0, ctx->n_patches, nq, nullptr, nullptr, nullptr, nullptr, &nb);
+  double *d_v = nullptr, *d_part = nullptr;   // second fine vector: Gauss rule (2 nq doubles) + 3 nb partial results
+  int rc = online_scratch(ctx, &d_v, &d_part, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  if ((int64_t)(2 * nq + 3 * (int64_t)nb) > n_fine) return fail(ctx, SLOD_ERR_UNSUPPORTED, "mesh too small for the scratch layout");
+  std::vector<double> part(3 * (size_t)nb);
+  cudaError_t e = cudaMemcpyAsync(d_v, v_fine, sizeof(double) * (size_t)n_fine, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_part, gx.data(), sizeof(double) * nq, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_part + nq, gw.data(), sizeof(double) * nq, cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess)
+    e = launch_fine_norms_reference(0, ctx->n_patches, nq, d_part, d_part + nq, d_v, d_part + 2 * nq, &nb);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(part.data(), d_part + 2 * nq, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return fail(ctx, SLOD_ERR_CUDA, std::string("slod_fine_norms_reference: ") + cudaGetErrorString(e));
+  double s2 = 0, sh = 0, mx = 0;
+  for (int i = 0; i < nb; ++i) {   // block order: reproducible
+    s2 += part[3 * (size_t)i];
+    sh += part[3 * (size_t)i + 1];
+    mx = std::max(mx, part[3 * (size_t)i + 2]);
+  }
+  if (l2) *l2 = std::sqrt(std::max(s2, 0.0));
+  if (linfty) *linfty = mx;
+  if (h1) *h1 = std::sqrt(std::max(s2 + sh, 0.0));
+  return SLOD_OK;
+}
+
+// ---- checkpoint: parameters + phi + A*phi (+ block-ELL coarse matrix) --------------------------------------------
+namespace {
+struct StateHeader {
+  char magic[8];          // "SLODB200"
+  int32_t version;
+  int32_t par[8];         // dim, spacedim, ref, n, ell, stabilize, problem, quirk
+  int64_t n_patches, stride, ell_width;
+  int32_t has_coarse;
+  int32_t pad;
+};
+}  // namespace
+
+int slod_save_state(slod_ctx *ctx, const char *path) {
+  if (!ctx || !path) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  StateHeader h{};
+  std::memcpy(h.magic, "SLODB200", 8);
+  h.version = 1;
+  const slod_params &p = ctx->par;
+  const int32_t pv[8] = {p.dim, p.spacedim, p.n_global_refinements, p.n_subdivisions, p.oversampling, p.stabilize ? 1 : 0,
+                         p.problem, p.quirk_presaved ? 1 : 0};
+  std::memcpy(h.par, pv, sizeof pv);
+  h.n_patches = ctx->n_patches;
+  h.stride = ctx->P.NfMax;
+  h.ell_width = ctx->P.ell_width;
+  h.has_coarse = ctx->coarse_done ? 1 : 0;
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return fail(ctx, SLOD_ERR_INVALID, std::string("cannot write ") + path);
+  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1;
+  const size_t nb = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax, nk = (size_t)ctx->n_patches * ctx->P.s * ctx->P.ell_width;
+  std::vector<double> buf(std::max(nb, h.has_coarse ? nk : (size_t)0));
+  for (const double *src : {(const double *)ctx->d_phi, (const double *)ctx->d_aphi}) {
+    if (cudaMemcpy(buf.data(), src, sizeof(double) * nb, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    ok = ok && std::fwrite(buf.data(), sizeof(double), nb, f) == nb;
+  }
+  if (h.has_coarse) {
+    if (cudaMemcpy(buf.data(), ctx->d_Kell, sizeof(double) * nk, cudaMemcpyDeviceToHost) != cudaSuccess) ok = false;
+    ok = ok && std::fwrite(buf.data(), sizeof(double), nk, f) == nk;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) return fail(ctx, SLOD_ERR_INVALID, std::string("write error on ") + path);
+  return SLOD_OK;
+}
+
+int slod_load_state(slod_ctx *ctx, const char *path) {
+  if (!ctx || !path) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  if (!ctx->subs.empty()) return fail(ctx, SLOD_ERR_UNSUPPORTED, "load a checkpoint into a single-device handle");
+  CK(cudaSetDevice(ctx->device));
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return fail(ctx, SLOD_ERR_INVALID, std::string("cannot read ") + path);
+  StateHeader h{};
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "SLODB200", 8) == 0 && h.version == 1;
+  const slod_params &p = ctx->par;
+  const int32_t pv[8] = {p.dim, p.spacedim, p.n_global_refinements, p.n_subdivisions, p.oversampling, p.stabilize ? 1 : 0,
+                         p.problem, p.quirk_presaved ? 1 : 0};
+  if (!ok || std::memcmp(h.par, pv, sizeof pv) != 0 || h.n_patches != ctx->n_patches || h.stride != ctx->P.NfMax ||
+      h.ell_width != ctx->P.ell_width) {
+    std::fclose(f);
+    return fail(ctx, SLOD_ERR_INVALID, "not a checkpoint of a handle with these parameters");
+  }
+  const size_t nb = (size_t)ctx->n_patches * ctx->P.s * ctx->P.NfMax, nk = (size_t)ctx->n_patches * ctx->P.s * ctx->P.ell_width;
+  if (!ctx->d_phi) {
+    CK(cudaMalloc(&ctx->d_phi, sizeof(double) * nb));
+    CK(cudaMalloc(&ctx->d_aphi, sizeof(double) * nb));
+  }
+  std::vector<double> buf(std::max(nb, h.has_coarse ? nk : (size_t)0));
+  for (double *dst : {ctx->d_phi, ctx->d_aphi}) {
+    ok = ok && std::fread(buf.data(), sizeof(double), nb, f) == nb;
+    if (ok && cudaMemcpy(dst, buf.data(), sizeof(double) * nb, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+  }
+  ctx->basis_done = ok;
+  ctx->coarse_done = false;
+  if (ok && h.has_coarse) {
+    if (!ctx->d_Kell) CK(cudaMalloc(&ctx->d_Kell, sizeof(double) * nk));
+    ok = std::fread(buf.data(), sizeof(double), nk, f) == nk;
+    if (ok && cudaMemcpy(ctx->d_Kell, buf.data(), sizeof(double) * nk, cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    std::fclose(f);
+    if (!ok) return fail(ctx, SLOD_ERR_INVALID, std::string("short read on ") + path);
+    int rc = build_csr_cache(ctx);
+    if (rc) return rc;
+    CK(launch_gather(0, ctx->d_Kell, ctx->d_perm, ctx->d_val, ctx->csr_nnz));
+    CK(cudaStreamSynchronize(0));
+    ctx->launches += 1;
+    ctx->coarse_done = true;
+    return SLOD_OK;
+  }
+  std::fclose(f);
+  if (!ok) return fail(ctx, SLOD_ERR_INVALID, std::string("short read on ") + path);
+  return SLOD_OK;
+}
+
 /* pinned host memory for the caller-owned output buffers (device->host copies into pageable memory run at a
  * fraction of the link speed) */
 int slod_alloc_host(size_t bytes, void **out) {

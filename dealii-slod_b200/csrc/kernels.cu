@@ -1268,6 +1268,14 @@ cudaError_t run_fp64_probe(int n_sm, double *dfma_tflops, double *dmma_tflops) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_fine_norms_reference(cudaStream_t st, long long n_cells, int nq, const double *gauss_x,
+                                        const double *gauss_w, const double *v, double *partial, int *n_blocks) {
+  const int nb = (int)((n_cells + kCgThreads - 1) / kCgThreads);
+  *n_blocks = nb;
+  if (partial) k_fine_norms_reference<<<nb, kCgThreads, 0, st>>>(n_cells, nq, gauss_x, gauss_w, v, partial);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay) {
   cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

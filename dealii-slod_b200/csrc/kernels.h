@@ -146,6 +146,8 @@ cudaError_t run_cg(cudaStream_t st, int nrows, const CgOperator &A, const double
                    long long *launches);
 cudaError_t launch_fine_quadratic_form(cudaStream_t st, int op, long long n_nodes, const double *d_coef, const double *x,
                                        double *partial, int *n_partial);
+cudaError_t launch_fine_norms_reference(cudaStream_t st, long long n_cells, int nq, const double *gauss_x,
+                                        const double *gauss_w, const double *v, double *partial, int *n_blocks);
 cudaError_t run_fp64_probe(int n_sm, double *dfma_tflops, double *dmma_tflops);
 cudaError_t launch_coarse(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi, const double *aphi,
                           double *Kell, const FinishLayout &lay);

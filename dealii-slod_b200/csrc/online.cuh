@@ -379,4 +379,78 @@ k_fine_apply(int op, long long n_nodes, const double *__restrict__ d_coef, const
   if (threadIdx.x == 0 && partial) partial[blockIdx.x] = dot;
 }
 
+// Norms the way the reference's error tables compute them (ParsedConvergenceTable::difference, source/LOD.cc:1252,
+// include/LOD.h:111-115): VectorTools::integrate_difference on the cells of dof_handler_fine -- the COARSE cells, each
+// carrying FE_Q_iso_Q1(n) -- with QGauss<dim>((degree + 1) * 2), degree = n, i.e. nq = 2 (n + 1) Gauss points per
+// direction and coarse cell, on which the piecewise multilinear function is evaluated sub-cell by sub-cell.  The rule
+// is not exact for Q_iso_Q1 functions (kinks inside the cell); slod_fine_norms has the exact values.
+// One thread per coarse cell; per block: sum of |v|^2 w, sum of |grad v|^2 w, max |v_c| over the points.
+__global__ void __launch_bounds__(kCgThreads)
+k_fine_norms_reference(long long n_cells, int nq, const double *__restrict__ gauss_x, const double *__restrict__ gauss_w,
+                       const double *__restrict__ v, double *__restrict__ partial) {
+  __shared__ double sRed[kCgThreads / 32];
+  const int dim = cP.dim, s = cP.s, n = cP.n, N = cP.N, G = cP.nsub + 1;
+  const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double l2 = 0.0, h1 = 0.0, linf = 0.0;
+  if (cell < n_cells) {
+    long long r = cell;
+    int c0[3] = {0, 0, 0};
+    for (int a = 0; a < dim; ++a) {
+      c0[a] = (int)(r % N);
+      r /= N;
+    }
+    const int nqz = (dim == 3) ? nq : 1;
+    for (int qz = 0; qz < nqz; ++qz)
+      for (int qy = 0; qy < nq; ++qy)
+        for (int qx = 0; qx < nq; ++qx) {
+          const int q[3] = {qx, qy, qz};
+          double w = 1.0, xi[3] = {0, 0, 0};
+          int o[3] = {0, 0, 0};
+          for (int a = 0; a < dim; ++a) {
+            w *= gauss_w[q[a]] * cP.H;
+            const double t = gauss_x[q[a]] * n;      // position in sub-cell units inside the coarse cell
+            int sub = (int)t;
+            if (sub > n - 1) sub = n - 1;
+            xi[a] = t - sub;
+            o[a] = c0[a] * n + sub;                  // global sub-cell index
+          }
+          for (int c = 0; c < s; ++c) {
+            double val = 0.0, gr[3] = {0, 0, 0};
+            for (int l = 0; l < (1 << dim); ++l) {
+              const int b[3] = {o[0] + (l & 1), o[1] + ((l >> 1) & 1), o[2] + ((l >> 2) & 1)};
+              const long long nb = ((long long)(dim == 3 ? b[2] : 0) * G + b[1]) * G + b[0];
+              const double u = v[nb * s + c];
+              double sh = 1.0;
+              for (int a = 0; a < dim; ++a) sh *= ((l >> a) & 1) ? xi[a] : 1.0 - xi[a];
+              val += u * sh;
+              for (int a = 0; a < dim; ++a) {
+                double g = (((l >> a) & 1) ? 1.0 : -1.0) / cP.h;
+                for (int a2 = 0; a2 < dim; ++a2)
+                  if (a2 != a) g *= ((l >> a2) & 1) ? xi[a2] : 1.0 - xi[a2];
+                gr[a] += u * g;
+              }
+            }
+            l2 += w * val * val;
+            for (int a = 0; a < dim; ++a) h1 += w * gr[a] * gr[a];
+            linf = fmax(linf, fabs(val));
+          }
+        }
+  }
+  l2 = block_sum(l2, sRed);
+  __syncthreads();
+  h1 = block_sum(h1, sRed);
+  __syncthreads();
+  // block maximum through the same scratch
+  for (int o = 16; o > 0; o >>= 1) linf = fmax(linf, __shfl_xor_sync(0xffffffffu, linf, o));
+  if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = linf;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int i = 0; i < kCgThreads / 32; ++i) m = fmax(m, sRed[i]);
+    partial[3 * blockIdx.x + 0] = l2;
+    partial[3 * blockIdx.x + 1] = h1;
+    partial[3 * blockIdx.x + 2] = m;
+  }
+}
+
 }  // namespace slod

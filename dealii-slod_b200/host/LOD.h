@@ -22,6 +22,8 @@
 
 #include <slod.h>
 
+#include "vtu.h"
+
 #include <chrono>
 #include <cctype>
 #include <cmath>
@@ -186,6 +188,7 @@ public:
     prm.declare(P + "/B200", "Device", "-1");              // [+] CUDA device ordinal, -1 = current
     prm.declare(P + "/B200", "Number of GPUs", "1");       // [+] devices driven by the one handle (NCCL inside the library)
     prm.declare(P + "/B200", "Write coarse matrix", "true");
+    prm.declare(P + "/B200", "Write VTU output", "true");  // [+] the reference always writes its three .vtu files
   }
   // ParameterAcceptor::initialize(prm_file): parse, or write a template and keep the defaults
   void initialize(const std::string &prm_file) {
@@ -215,6 +218,7 @@ public:
     device = (int)prm.get_integer(P + "/B200", "Device");
     n_gpus = (int)nonneg(prm.get_integer(P + "/B200", "Number of GPUs"), "Number of GPUs");
     write_coarse_matrix = prm.get_bool(P + "/B200", "Write coarse matrix");
+    write_vtu = prm.get_bool(P + "/B200", "Write VTU output");
     (void)rhs_constants();   // refuse what this host cannot evaluate before any work is done
   }
 
@@ -238,6 +242,7 @@ public:
   int device = -1;
   int n_gpus = 1;
   bool write_coarse_matrix = true;
+  bool write_vtu = true;
 
   // the constant value of every component of the right-hand side; anything but numbers is refused
   std::vector<double> rhs_constants() const {
@@ -382,18 +387,22 @@ public:
     make_fe();
     initialize_patches();
     create_random_problem_coefficients();
+    output_coefficients();
     compute_basis_function_candidates();
     assemble_global_matrix();
     assemble_and_solve_fem_problem();
     solve();
     compare_lod_with_fem();
-    // output_fine_results / output_coarse_results (VTU writers) are out of scope
+    output_coarse_results();
+    output_fine_results();
     output_offline_results();
     if (par.solve_fine_problem) {   // source/LOD.cc:1463-1465
       pcout << "SLOD vs reference FEM(h)" << std::endl;
       char buf[200];
-      std::snprintf(buf, sizeof buf, "cells dofs   u_L2_norm    u_H1_norm    u_energy_norm\n%5lld %6zu %12.6e %12.6e %12.6e",
-                    (long long)n_patches, n_dofs_fine, error_LOD_FEMh[0], error_LOD_FEMh[1], error_LOD_FEMh[2]);
+      std::snprintf(buf, sizeof buf,
+                    "cells dofs   u_L2_norm    u_Linfty_norm u_H1_norm    u_energy_norm\n%5lld %6zu %12.6e %12.6e %12.6e %12.6e",
+                    (long long)n_patches, n_dofs_fine, error_LOD_FEMh[0], error_LOD_FEMh[1], error_LOD_FEMh[2],
+                    error_LOD_FEMh[3]);
       pcout << buf << std::endl;
     }
     computing_timer.print_summary(pcout);
@@ -570,11 +579,15 @@ protected:
     TimerOutput::Scope t(computing_timer, "5: compare FEM vs LOD (B200)");
     std::vector<double> diff(n_dofs_fine);
     for (size_t i = 0; i < n_dofs_fine; ++i) diff[i] = fem_solution[i] - lod_solution[i];
-    double l2 = 0, h1s = 0, en = 0;
-    check(slod_fine_norms(slod, diff.data(), &l2, &h1s, &en), "slod_fine_norms");
+    // par.error_LOD_FEMh.difference(dh, fem_solution, lod_solution) (source/LOD.cc:1252): the table's default norms
+    // L2, Linfty, H1 with the reference's quadrature; [+] the energy norm of the problem's own bilinear form (exact)
+    double l2 = 0, linf = 0, h1 = 0, en = 0;
+    check(slod_fine_norms_reference(slod, diff.data(), &l2, &linf, &h1), "slod_fine_norms_reference");
+    check(slod_fine_norms(slod, diff.data(), nullptr, nullptr, &en), "slod_fine_norms");
     error_LOD_FEMh[0] = l2;
-    error_LOD_FEMh[1] = std::sqrt(l2 * l2 + h1s * h1s);   // deal.II's H1_norm is the full norm
-    error_LOD_FEMh[2] = en;
+    error_LOD_FEMh[1] = linf;
+    error_LOD_FEMh[2] = h1;
+    error_LOD_FEMh[3] = en;
   }
 
   void solve() {  // source/LOD.cc:975-1001
@@ -604,6 +617,67 @@ protected:
     char buf[128];
     std::snprintf(buf, sizeof buf, "   lod solution l2 norm = %.12e", std::sqrt(nrm));
     pcout << buf << std::endl;
+  }
+
+  // <name>_coefficients.vtu (include/Diffusion.h:70-108): the coefficient fields as cell data on the fine sub-cell mesh
+  // of (2^ref n)^dim cells, sampled at the cell centres like VectorTools::interpolate on FE_DGQ(0) does
+  void output_coefficients() {
+    if (!par.write_vtu) return;
+    const int nc = (int)((1u << par.n_global_refinements) * par.n_subdivisions);
+    const size_t ncell = (size_t)std::pow((double)nc, dim);
+    const char *names[2] = {spacedim == 1 ? "alpha" : "lambda", "mu"};
+    std::vector<std::vector<double>> vals(n_coefficient_fields(), std::vector<double>(ncell));
+    for (unsigned f = 0; f < n_coefficient_fields(); ++f)
+      for (size_t c = 0; c < ncell; ++c) {
+        size_t r = c;
+        double p[3] = {0, 0, 0};
+        for (int a = 0; a < dim; ++a) {
+          p[a] = ((double)(r % nc) + 0.5) / nc;
+          r /= nc;
+        }
+        vals[f][c] = coefficient(f).value(p);
+      }
+    std::vector<vtu::Field> cell;
+    for (unsigned f = 0; f < n_coefficient_fields(); ++f) cell.push_back({names[f], 1, vals[f].data()});
+    vtu::write(par.output_directory + "/" + par.output_name + "_coefficients.vtu", dim, nc, {}, cell);
+  }
+
+  // <name>_coarse.vtu (source/LOD.cc:248-293): the coarse solution, one value per cell and component (FE_DGQ(0)^s),
+  // and the exact solution interpolated the same way (constant expressions only on this host)
+  void output_coarse_results() {
+    if (!par.write_vtu) return;
+    const int N = 1 << par.n_global_refinements;
+    const size_t ncell = (size_t)n_patches;
+    std::vector<double> sol(ncell * spacedim), exact(ncell * spacedim, 0.0);
+    for (size_t c = 0; c < ncell; ++c) {   // lexicographic cell -> patch id (Morton)
+      size_t r = c, code = 0;
+      int idx[3] = {0, 0, 0};
+      for (int a = 0; a < dim; ++a) {
+        idx[a] = (int)(r % N);
+        r /= N;
+      }
+      for (unsigned b = 0; b < par.n_global_refinements; ++b)
+        for (int a = 0; a < dim; ++a) code |= (size_t)((idx[a] >> b) & 1) << (dim * b + a);
+      for (int d = 0; d < spacedim; ++d) sol[c * spacedim + d] = solution[code * spacedim + d];
+    }
+    vtu::write(par.output_directory + "/" + par.output_name + "_coarse.vtu", dim, N, {},
+               {{"LOD_solution", spacedim, sol.data()}, {"exact_solution", spacedim, exact.data()}});
+  }
+
+  // <name>_fine.vtu (source/LOD.cc:1262-1377): fem_reference, exact_rhs and lod_solution as point data on the fine
+  // grid.  Every sub-cell is written (the reference's build_patches() keeps the coarse-cell vertices only); the
+  // coarse FEM solution of the reference's table is not computed by this host.
+  void output_fine_results() {
+    if (!par.write_vtu) return;
+    const int nc = (int)((1u << par.n_global_refinements) * par.n_subdivisions);
+    std::vector<double> rhs_nodal(n_dofs_fine);
+    const std::vector<double> fc = par.rhs_constants();
+    for (size_t i = 0; i < n_dofs_fine; ++i) rhs_nodal[i] = fc[i % spacedim];
+    std::vector<vtu::Field> pt;
+    if (par.solve_fine_problem) pt.push_back({"fem_reference", spacedim, fem_solution.data()});
+    pt.push_back({"exact_rhs", spacedim, rhs_nodal.data()});
+    pt.push_back({"lod_solution", spacedim, lod_solution.data()});
+    vtu::write(par.output_directory + "/" + par.output_name + "_fine.vtu", dim, nc, pt, {});
   }
 
   void output_offline_results() {
@@ -639,7 +713,7 @@ protected:
   CoarseMatrix global_stiffness_matrix;
   // include/LOD.h:236-239, lexicographic fine numbering
   std::vector<double> fem_rhs, fem_solution, system_rhs, solution, lod_solution;
-  double error_LOD_FEMh[3] = {0, 0, 0};   // L2, H1, energy norm of fem_solution - lod_solution (include/LOD.h:115)
+  double error_LOD_FEMh[4] = {0, 0, 0, 0};   // L2, Linfty, H1 (reference quadrature), energy norm of fem_solution - lod_solution (include/LOD.h:115)
 };
 
 // include/Diffusion.h:56-306.  The reference draws Alpha(1,100,8) in the constructor; here the table is drawn in

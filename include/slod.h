@@ -157,6 +157,20 @@ int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t 
  * reference integrates |u_fem - u_lod| with a Gauss rule on the coarse cells (ParsedConvergenceTable::difference),
  * which is not exact for Q_iso_Q1 functions; these are the exact values of the same norms. */
 int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_semi, double *energy);
+/* The same norms the way the reference's error tables compute them (ParsedConvergenceTable::difference,
+ * source/LOD.cc:1252; include/LOD.h:111-115): VectorTools::integrate_difference with QGauss((degree + 1) * 2) on the cells
+ * of dof_handler_fine, i.e. 2 (n_subdivisions + 1) Gauss points per direction on every COARSE cell; norms of the table's
+ * default list: L2_norm, Linfty_norm (maximum over the quadrature points and components), H1_norm (the full norm
+ * sqrt(L2^2 + |.|_H1^2)).  Outputs may be NULL. */
+int slod_fine_norms_reference(slod_ctx *ctx, const double *v_fine, double *l2, double *linfty, double *h1);
+
+/* ---- checkpoint of the offline phase (the reference has none: it recomputes every run) ----------
+ * slod_save_state writes the parameters, the basis (phi, A*phi) and, if assembled, the coarse matrix to one binary
+ * file; slod_load_state restores them into a handle created with the SAME parameters (else SLOD_ERR_INVALID), after
+ * which the online entry points (slod_coarse_rhs / _solve / slod_prolongate, slod_get_basis, slod_get_coarse_csr) work
+ * without recomputing anything.  The coefficient is not part of the file (slod_fem_solve / slod_fine_norms need it set). */
+int slod_save_state(slod_ctx *ctx, const char *path);
+int slod_load_state(slod_ctx *ctx, const char *path);
 
 /* Page-locked host memory for the caller-owned output buffers of slod_get_all_basis / slod_get_coarse_csr: copies
  * into pageable memory work too but run at a fraction of the link speed.  No reference counterpart. */

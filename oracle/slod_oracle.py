@@ -726,6 +726,46 @@ class SlodOracle:
         eye = sp.identity(s)
         return sp.kron(M, eye).tocsr(), sp.kron(L, eye).tocsr()
 
+    def reference_error_norms(self, v):
+        """(L2_norm, Linfty_norm, H1_norm) of a fine vector the way ParsedConvergenceTable::difference computes them
+        (source/LOD.cc:1252, include/LOD.h:111-115): VectorTools::integrate_difference against zero on the cells of
+        dof_handler_fine -- the coarse cells with FE_Q_iso_Q1(n) -- with QGauss((degree + 1) * 2) = 2 (n + 1) points per
+        direction [deal.II 9.6 parsed_convergence_table: q_gauss((dh.get_fe().degree + 1) * 2)]; default norm list
+        L2, Linfty, H1 (full norm).  Lexicographic numbering node * spacedim + comp."""
+        pr = self.prob
+        dim, s, n, N, h, H = pr.dim, pr.spacedim, pr.n_subdivisions, pr.N, pr.h, pr.H
+        G = N * n + 1
+        nq = 2 * (n + 1)
+        gx, gw = np.polynomial.legendre.leggauss(nq)
+        gx, gw = 0.5 * (gx + 1.0), 0.5 * gw
+        V = np.asarray(v, dtype=float).reshape((G,) * dim + (s,))     # [z][y][x][comp]
+        t = gx * n
+        sub = np.minimum(t.astype(int), n - 1)
+        xi = t - sub
+        l2 = h1 = 0.0
+        linf = 0.0
+        for cell in itertools.product(range(N), repeat=dim):          # (x, y, z)
+            for q in itertools.product(range(nq), repeat=dim):
+                w = np.prod([gw[q[a]] * H for a in range(dim)])
+                o = [cell[a] * n + sub[q[a]] for a in range(dim)]
+                val = np.zeros(s)
+                grad = np.zeros((dim, s))
+                for l in itertools.product(range(2), repeat=dim):
+                    idx = tuple(o[a] + l[a] for a in reversed(range(dim)))
+                    u = V[idx]
+                    sh = np.prod([xi[q[a]] if l[a] else 1.0 - xi[q[a]] for a in range(dim)])
+                    val += u * sh
+                    for a in range(dim):
+                        g = (1.0 if l[a] else -1.0) / h
+                        for a2 in range(dim):
+                            if a2 != a:
+                                g *= xi[q[a2]] if l[a2] else 1.0 - xi[q[a2]]
+                        grad[a] += u * g
+                l2 += w * float(val @ val)
+                h1 += w * float((grad * grad).sum())
+                linf = max(linf, float(np.abs(val).max()))
+        return math.sqrt(l2), linf, math.sqrt(l2 + h1)
+
     # -- LOD::solve (source/LOD.cc:975-1001) and the prolongation (source/LOD.cc:1251) -----------------------------
     @staticmethod
     def solve_coarse(K, b, max_steps=100, tolerance=1e-10, reduction=1e-10, omega=1.2, direct=False):

@@ -55,6 +55,21 @@ def test_fem_solve_and_norms(case):
     assert abs(l2 - np.sqrt(v @ (M @ v))) <= 1e-12 * l2
     assert abs(h1 - np.sqrt(v @ (L @ v))) <= 1e-12 * h1
     assert abs(en - np.sqrt(v @ (A @ v))) <= 1e-12 * en
+    # the reference's own error-table quadrature (ParsedConvergenceTable::difference, source/LOD.cc:1252): QGauss on the
+    # coarse cells -- against the oracle's restatement, and close to (but not equal to) the exact norms of a smooth field
+    if ctx.n_patches <= 512:
+        r_l2, r_inf, r_h1 = ctx.fine_norms_reference(v)
+        o_l2, o_inf, o_h1 = orc.reference_error_norms(v)
+        assert abs(r_l2 - o_l2) <= 1e-12 * o_l2 and abs(r_h1 - o_h1) <= 1e-12 * o_h1 and abs(r_inf - o_inf) <= 1e-12 * o_inf
+    xs = np.linspace(0.0, 1.0, G)
+    smooth = np.sin(2.0 * xs)
+    for _ in range(dim - 1):
+        smooth = np.multiply.outer(np.cos(xs), smooth)
+    smooth = np.repeat(smooth.ravel(), s)
+    e_l2, e_h1s, _ = ctx.fine_norms(smooth)
+    r_l2, r_inf, r_h1 = ctx.fine_norms_reference(smooth)
+    assert abs(r_l2 - e_l2) <= 1e-3 * e_l2 and abs(r_h1 - np.hypot(e_l2, e_h1s)) <= 1e-2 * r_h1
+    assert r_inf <= np.abs(smooth).max() * (1 + 1e-12)
     ctx.close()
 
 

@@ -138,10 +138,31 @@ def test_apps_match_oracle(apps, tmp_path, app, dim, s, ref, ell, r):
     # compare_lod_with_fem (source/LOD.cc:1240-1260): the SLOD vs FEM(h) table
     assert f"size of fem u {s * (2 ** ref * 2 + 1) ** dim}" in out
     u_fem, A = orc.fem_solve(f)
-    M, L = orc.fine_norm_matrices()
     e = u_fem - C @ u
     row = out.split("SLOD vs reference FEM(h)")[1].split("\n")[2].split()
-    l2, h1, en = float(row[2]), float(row[3]), float(row[4])
-    assert abs(l2 - np.sqrt(e @ (M @ e))) <= 1e-4 * l2
-    assert abs(h1 - np.sqrt(e @ (M @ e) + e @ (L @ e))) <= 1e-4 * h1
+    l2, linf, h1, en = float(row[2]), float(row[3]), float(row[4]), float(row[5])
+    # the table's L2 / Linfty / H1 columns follow ParsedConvergenceTable::difference (the reference's quadrature)
+    o_l2, o_inf, o_h1 = orc.reference_error_norms(e)
+    assert abs(l2 - o_l2) <= 1e-4 * l2 and abs(linf - o_inf) <= 1e-4 * linf and abs(h1 - o_h1) <= 1e-4 * h1
     assert abs(en - np.sqrt(e @ (A @ e))) <= 1e-4 * en
+    # the three .vtu files of the reference (include/Diffusion.h:102-105, source/LOD.cc:284-286, :1370-1372)
+    nsub = 2 ** ref * 2
+    for name, npts, ncells, fields in (("t_coefficients.vtu", (nsub + 1) ** dim, nsub ** dim, ["alpha" if s == 1 else "lambda"]),
+                                       ("t_coarse.vtu", (2 ** ref + 1) ** dim, (2 ** ref) ** dim, ["LOD_solution", "exact_solution"]),
+                                       ("t_fine.vtu", (nsub + 1) ** dim, nsub ** dim, ["fem_reference", "exact_rhs", "lod_solution"])):
+        txt = (tmp_path / name).read_text()
+        assert f'NumberOfPoints="{npts}" NumberOfCells="{ncells}"' in txt
+        for fld in fields:
+            assert f'Name="{fld}"' in txt
+    # the coarse VTU carries the coarse solution in lexicographic cell order
+    import xml.etree.ElementTree as ET
+    arr = [a for a in ET.parse(tmp_path / "t_coarse.vtu").getroot().iter("DataArray") if a.get("Name") == "LOD_solution"][0]
+    vals = np.array(arr.text.split(), dtype=float).reshape((2 ** ref) ** dim, -1)[:, :s]
+    N = 2 ** ref
+    lex = np.arange(N ** dim)
+    code = np.zeros_like(lex)
+    for a in range(dim):
+        ia = (lex // N ** a) % N
+        for b in range(ref):
+            code |= ((ia >> b) & 1) << (dim * b + a)
+    assert np.abs(vals.ravel() - u.reshape(-1, s)[code].ravel()).max() <= 1e-6 * np.abs(u).max()

@@ -21,9 +21,9 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-def _run(n_gpus, case, tab):
+def _run(n_gpus, case, tab, r):
     ctx = pkg.SlodContext(stabilize=True, n_gpus=n_gpus, device=0, **case)
-    ctx.set_coefficient(0, 5, tab)
+    ctx.set_coefficient(0, r, tab)
     ctx.compute_basis()
     ctx.assemble_coarse()
     phi, aphi = ctx.all_basis()
@@ -41,10 +41,11 @@ def test_one_handle_drives_all_gpus(case):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     dim = case["dim"]
-    tab = 1.0 + 99.0 * np.random.default_rng(5).random((2 ** 5) ** dim)
-    ref = _run(1, case, tab)
+    r = case["n_global_refinements"] + 1          # one table cell per fine sub-cell
+    tab = 1.0 + 99.0 * np.random.default_rng(5).random((2 ** r) ** dim)
+    ref = _run(1, case, tab, r)
     for ng in sorted({2, n}):
-        got = _run(ng, case, tab)
+        got = _run(ng, case, tab, r)
         for a, b in zip(ref[:5], got[:5]):
             assert np.array_equal(a, b)
         assert got[5][0] > 0

@@ -217,3 +217,38 @@ def test_solver_control_errors():
     u, steps, _ = ctx.coarse_solve(np.zeros(ctx.n_patches))      # zero rhs: converged at step 0
     assert steps == 0 and not u.any()
     ctx.close()
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """slod_save_state / slod_load_state: a fresh handle with the same parameters serves the basis, the
+    coarse matrix and the online phase from the file, bit-identically, without recomputing; wrong parameters are refused."""
+    ctx, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2)
+    ctx.compute_basis()
+    ctx.assemble_coarse()
+    f = np.random.default_rng(1).standard_normal(ctx.n_fine)
+    b = ctx.coarse_rhs(f)
+    u, steps, _ = ctx.coarse_solve(b, max_steps=5000, tolerance=0.0, reduction=1e-12)
+    uh = ctx.prolongate(u)
+    path = str(tmp_path / "offline.slod")
+    ctx.save_state(path)
+    phi, aphi = (x.copy() for x in ctx.all_basis())
+    val = ctx.coarse_csr()[2].copy()
+    ctx.close()
+    ctx2 = pkg.SlodContext(dim=2, spacedim=1, n_global_refinements=4, n_subdivisions=2, oversampling=2, stabilize=True)
+    with pytest.raises(pkg.SlodError):
+        ctx2.coarse_rhs(f)                      # nothing computed yet
+    ctx2.load_state(path)
+    p2, a2 = ctx2.all_basis()
+    assert np.array_equal(p2, phi) and np.array_equal(a2, aphi)
+    assert np.array_equal(ctx2.coarse_csr()[2], val)
+    b2 = ctx2.coarse_rhs(f)
+    u2, steps2, _ = ctx2.coarse_solve(b2, max_steps=5000, tolerance=0.0, reduction=1e-12)
+    assert np.array_equal(b2, b) and steps2 == steps and np.array_equal(u2, u)
+    assert np.array_equal(ctx2.prolongate(u2), uh)
+    launches = ctx2.launch_count
+    ctx2.close()
+    other = pkg.SlodContext(dim=2, spacedim=1, n_global_refinements=4, n_subdivisions=2, oversampling=1, stabilize=True)
+    with pytest.raises(pkg.SlodError):
+        other.load_state(path)
+    other.close()
+    assert launches < 400                       # CG launches only: no patch kernels ran on the second handle
