@@ -429,9 +429,14 @@ def main():
     # ---- N > 1: the distributed result against a single-GPU recomputation on rank 0 (outside the timed region) ----
     multi_gpu_check = None
     _dbg("e2e done")
+    if os.environ.get("SLOD_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(45, exit=True)
     if world > 1:
-        step()
+        ctx.offline_distributed(phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), gather_phi=True, gather_K=True, stream=stream)
+        ctx.synchronize()
         torch.cuda.synchronize()
+        _dbg("check: distributed step done")
         if rank == 0:
             # patches of a sub-range that straddles the first partition boundary, recomputed by this rank alone into
             # fresh buffers; the coarse rows of the range need A*phi of their neighbours: take it from the gathered array
@@ -439,8 +444,10 @@ def main():
             q0, q1 = p1 - half, min(n, p1 + half)
             phi2 = torch.zeros_like(phi)
             aphi2 = torch.zeros_like(aphi)
+            _dbg("check: buffers allocated")
             ctx.compute_basis_device(q0, q1, phi2.data_ptr(), aphi2.data_ptr(), stream)
             ctx.synchronize()
+            _dbg("check: basis recomputed")
             same_phi = bool(torch.equal(phi2[q0:q1], phi[q0:q1]))
             same_aphi = bool(torch.equal(aphi2[q0:q1], aphi[q0:q1]))
             K2 = torch.zeros_like(K)

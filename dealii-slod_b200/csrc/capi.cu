@@ -135,6 +135,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -163,6 +164,7 @@ NcclApi *nccl_api() {
     api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
     api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
@@ -1123,7 +1125,9 @@ void slod_destroy(slod_ctx *ctx) {
   ctx->subs.clear();
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();   // slod_assemble_coarse only enqueues
-  if (ctx->comm) nccl_api()->CommDestroy(ctx->comm);
+  // everything this handle enqueued has completed (synchronised above).  Abort instead of Destroy: Destroy waits for
+  // the peers, and a handle that is torn down on an error path (one rank failed) must not hang the process
+  if (ctx->comm) nccl_api()->CommAbort(ctx->comm);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   free_dev(ctx);
   for (auto &ev : ctx->ev)
