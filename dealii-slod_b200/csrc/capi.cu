@@ -68,6 +68,7 @@ struct slod_ctx {
   bool split_solver = false;      // factor + triangular-solve kernels instead of the fused solver (large 3-D patches)
   size_t smem_factor = 0, smem_tri = 0;
   double *d_Lrec = nullptr;       // factor records of a chunk
+  double *d_stw = nullptr;        // per-CTA stencil scratch of k_patch_factor
   cudaEvent_t ev_split = nullptr;
   float split_factor_ms = 0;
   long long mma_lws_per_cta = 0;
@@ -414,7 +415,7 @@ void free_workspace(slod_ctx *c) {
     p = nullptr;
   };
   F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
-  F(c->d_Lrec);
+  F(c->d_Lrec); F(c->d_stw);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
   c->chunk = 0;
   c->ids_cap = 0;
@@ -454,7 +455,10 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
     CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
     if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
     if (ctx->split_solver)
+    {
       CK(cudaMalloc(&ctx->d_Lrec, sizeof(double) * (size_t)split_rec_stride(ctx->mma_nip) * chunk));
+      CK(cudaMalloc(&ctx->d_stw, sizeof(double) * split_stencil_ws_doubles(2 * ctx->n_sm, ctx->mma_nip)));
+    }
     else
       CK(cudaMalloc(&ctx->d_Lws, sizeof(double) * (size_t)ctx->sl.lws_per_cta * ctx->grid_solve));
     // selection pipeline: work lists for every (patch, component) of a chunk, eigen buffers for one round
@@ -544,7 +548,7 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
     if (ctx->split_solver) {
       static const int factor_grid_env = getenv("SLOD_FACTOR_GRID") ? atoi(getenv("SLOD_FACTOR_GRID")) : 0;   // experiments
       CK(launch_patch_factor(std::min(nw, factor_grid_env > 0 ? factor_grid_env : 2 * ctx->n_sm), ctx->smem_factor, st, ids, nw, ctx->d_coef, ctx->d_Lrec,
-                             ctx->d_status, ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
+                             ctx->d_stw, ctx->d_status, ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
       if (ci == 0) CK(cudaEventRecord(ctx->ev_split, st));
       CK(launch_patch_trisolve(std::min(nw, ctx->n_sm), ctx->smem_tri, st, ids, nw, ctx->d_Lrec, ctx->d_X,
                                ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, wc));
@@ -1926,7 +1930,7 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   const int id = (int)patch;
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));
   if (ctx->split_solver) {
-    CK(launch_patch_factor(1, ctx->smem_factor, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_Lrec, ctx->d_status,
+    CK(launch_patch_factor(1, ctx->smem_factor, 0, ctx->d_ids, 1, ctx->d_coef, ctx->d_Lrec, ctx->d_stw, ctx->d_status,
                            ctx->sl.coef_doubles, ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, nullptr));
     CK(launch_patch_trisolve(1, ctx->smem_tri, 0, ctx->d_ids, 1, ctx->d_Lrec, ctx->d_X, ctx->sl.coef_doubles,
                              ctx->mma_nip, ctx->sl.ldx, ctx->sl.x_stride, nullptr));

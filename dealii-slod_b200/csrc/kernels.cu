@@ -974,7 +974,7 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
 constexpr int kSplitRB = 13, kFactorWarps = 8, kTriWarps = 16;
 size_t split_factor_smem(int coef_doubles, int nip_max) {
   const int R = 8 * kSplitRB, LDWF = (R % 16 == 8) ? R : R + 8, LDP = R + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * 64 + 64 + 256) +
+  return sizeof(double) * ((size_t)coef_doubles + (size_t)R * LDWF + 8 * LDP + 2 * 64 + 64) +
          sizeof(int) * ((size_t)nip_max + kSplitRB * (kSplitRB - 1) / 2 + 16 + 8);
 }
 size_t split_trisolve_smem(int nip_max) {
@@ -982,9 +982,10 @@ size_t split_trisolve_smem(int nip_max) {
          sizeof(int) * ((size_t)nip_max + 8 * kTriWarps + kTriWarps + nip_max / 8 + 1 + 8 + 4);
 }
 long long split_rec_stride(int nip_max) { return (long long)(nip_max / 8) * kSplitRB * 64; }
+size_t split_stencil_ws_doubles(int grid, int nip_max) { return (size_t)grid * nip_max * 14; }
 cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                                double *Lrec, int *status, int coef_doubles, int nip_max, int ldx, long long x_stride,
-                                int *work_counter) {
+                                double *Lrec, double *stencil_ws, int *status, int coef_doubles, int nip_max, int ldx,
+                                long long x_stride, int *work_counter) {
   SplitLayout lay{coef_doubles, nip_max, ldx, x_stride, split_rec_stride(nip_max)};
   cudaError_t e = cudaFuncSetAttribute(k_patch_factor<kSplitRB, kFactorWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -998,7 +999,7 @@ cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const in
     printf("k_patch_factor: %d CTAs/SM, %zu B dynamic shared memory\n", nb, smem);
   }
   if (work_counter && (e = cudaMemsetAsync(work_counter, 0, sizeof(int), st)) != cudaSuccess) return e;
-  k_patch_factor<kSplitRB, kFactorWarps><<<grid, 32 * kFactorWarps, smem, st>>>(ids, n_work, coef, Lrec, status, lay, work_counter);
+  k_patch_factor<kSplitRB, kFactorWarps><<<grid, 32 * kFactorWarps, smem, st>>>(ids, n_work, coef, Lrec, stencil_ws, status, lay, work_counter);
   return cudaGetLastError();
 }
 cudaError_t launch_patch_trisolve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Lrec,

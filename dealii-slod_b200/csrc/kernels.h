@@ -65,9 +65,10 @@ cudaError_t launch_patch_solve_mma(int variant, int grid, size_t smem, cudaStrea
 size_t split_factor_smem(int coef_doubles, int nip_max);
 size_t split_trisolve_smem(int nip_max);
 long long split_rec_stride(int nip_max);
+size_t split_stencil_ws_doubles(int grid, int nip_max);   // per-CTA stencil scratch of k_patch_factor
 cudaError_t launch_patch_factor(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
-                                double *Lrec, int *status, int coef_doubles, int nip_max, int ldx, long long x_stride,
-                                int *work_counter);
+                                double *Lrec, double *stencil_ws, int *status, int coef_doubles, int nip_max, int ldx,
+                                long long x_stride, int *work_counter);
 cudaError_t launch_patch_trisolve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *Lrec,
                                   double *X, int coef_doubles, int nip_max, int ldx, long long x_stride, int *work_counter);
 cudaError_t launch_patch_dense(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,

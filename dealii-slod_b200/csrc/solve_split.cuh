@@ -122,7 +122,8 @@ __device__ __forceinline__ double stiff_entry_3d(const Geom &g, const double *sC
 template <int RBMAX, int NW>
 __global__ void __launch_bounds__(32 * NW, 2)
 k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
-               double *__restrict__ Lrec, int *__restrict__ status, SplitLayout lay, int *work_counter) {
+               double *__restrict__ Lrec, double *__restrict__ stencil_ws, int *__restrict__ status, SplitLayout lay,
+               int *work_counter) {
   constexpr int R = 8 * RBMAX;
   constexpr int LDWF = (R % 16 == 8) ? R : R + 8;  // row stride with LDWF % 16 == 8 : conflict-free C fragments
   constexpr int LDP = R + 4;                        // k-major panel copy
@@ -135,8 +136,7 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
   double *sLpT = sWf + R * LDWF;            // [8][LDP]  panel, k-major, slot rows
   double *sLinv = sLpT + 8 * LDP;           // [2][64]
   double *sK = sLinv + 2 * 64;              // [64] reference sub-cell matrix
-  double *sStage = sK + 64;                 // [2][128] lower-stencil entries of the block row entering the window next
-  int *sRowPk = (int *)(sStage + 256);      // [nip_max] packed node coords / mask
+  int *sRowPk = (int *)(sK + 64);           // [nip_max] packed node coords / mask
   int *sTileTab = sRowPk + lay.nip_max;     // [NTT] (offI | offJ << 8) of the trailing-update tiles
   int *sDOff = sTileTab + NTT;              // [16] dof offset of each lower stencil slot
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,6 +160,10 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
     int RB = (bw + 8 + 7) >> 3;
     if (RB > RBMAX) RB = RBMAX;  // host guarantees bw_max fits
     double *rec = Lrec + (size_t)w * lay.rec_stride;
+    // lower-stencil entries of every row of this patch, 8 * (nlow + 1) per block row: computed by all threads in the
+    // prologue into a per-CTA scratch in global memory (stays in L2), consumed block row by block row as the window
+    // slides -- computing them on the fly in the loop put 1.2 k cycles per step on one warp
+    double *stw = stencil_ws + (size_t)blockIdx.x * lay.nip_max * (nlow + 1);
     __syncthreads();
     load_coef(geo, d_coef, sCoef);
     for (int r = tid; r < 8 * NBLK; r += NT) {
@@ -205,39 +209,38 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
       lower_offset(e, dl);
       return stiff_entry_3d(geo, sCoef, sK, n, a, dl);
     };
-    // ... and their scatter into block row slot sB of the window; `val` holds the 112 entries of the block
-    auto scatter_block_row = [&](int blk, int sB, const double *val, int item0, int nitem) {
-      for (int item = item0; item < 8 * (nlow + 1); item += nitem) {
-        const int i = item & 7, e = item >> 3;
-        const int r = 8 * blk + i;
-        const int pk = sRowPk[r];
-        if (pk < 0) {  // bit 31: a real dof row
-          if (!((pk >> (16 + e)) & 1)) continue;
-          const int c = r + sDOff[e];
-          int sb = sB - (blk - (c >> 3));
-          if (sb < 0) sb += RB;
-          sWf[(8 * sB + i) * LDWF + 8 * sb + (c & 7)] = val[item];
-        } else if (e == 0) {
-          sWf[(8 * sB + i) * LDWF + 8 * sB + i] = 1.0;
-        }
+    // ... and the scatter of one of them into block row slot sB of the window
+    auto scatter_item = [&](int blk, int sB, int item, double v) {
+      const int i = item & 7, e = item >> 3;
+      const int r = 8 * blk + i;
+      const int pk = sRowPk[r];
+      if (pk < 0) {  // bit 31: a real dof row
+        if (!((pk >> (16 + e)) & 1)) return;
+        const int c = r + sDOff[e];
+        int sb = sB - (blk - (c >> 3));
+        if (sb < 0) sb += RB;
+        sWf[(8 * sB + i) * LDWF + 8 * sb + (c & 7)] = v;
+      } else if (e == 0) {
+        sWf[(8 * sB + i) * LDWF + 8 * sB + i] = 1.0;
       }
     };
 
     for (int b = 0; b < RB && b < NBLK; ++b) zero_block_row(b);
+    for (int item = tid; item < NBLK * 8 * (nlow + 1); item += NT)
+      __stcg(stw + item, stencil_item(item / (8 * (nlow + 1)), item % (8 * (nlow + 1))));
     __syncthreads();
-    for (int b = 0; b < RB && b < NBLK; ++b) {   // the first RB block rows, through the staging buffer
-      if (tid < 8 * (nlow + 1)) sStage[tid] = stencil_item(b, tid);
-      __syncthreads();
-      scatter_block_row(b, b, sStage, tid, NT);
-      __syncthreads();
+    for (int b = 0; b < RB && b < NBLK; ++b) {   // the first RB block rows of the window
+      for (int item = tid; item < 8 * (nlow + 1); item += NT) {
+        const double v = __ldcg(stw + b * 8 * (nlow + 1) + item);
+        scatter_item(b, b, item, v);
+      }
     }
-    if (RB < NBLK && tid < 8 * (nlow + 1)) sStage[128 * (RB & 1) + tid] = stencil_item(RB, tid);   // block entering at step 0
     __syncthreads();
     int bad = 0;
     if (warp == 0) bad |= chol8_inv_reg(sWf, LDWF, lane, sLinv);
     __syncthreads();
 
-    PHS_DECL(0, 3, NW - 1)
+    PHS_DECL(0, 3, 4)
     // One step = one full barrier.  Roles:
     //   warp 0        the critical chain: panel tile (k+1, k), update and factorisation of the next diagonal tile --
     //                 started at the top of the step, without waiting for the other panel tiles;
@@ -245,7 +248,16 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
     //                 pipe: record tile 0, window slide (zero + refill of the freed block row, next block staged);
     //   other warps   panel tiles 2 .. nl, a named barrier among them and warp 0 (tile 1), trailing tiles.
     constexpr int NTW = NW - NW / 4;          // panel / trailing warps
-    constexpr int NBAR = 32 * (NTW + 1);      // threads of the named barrier: those warps + warp 0
+    constexpr int NBAR = 32 * (NTW + 1);      // named barrier 1: those warps (sync) + warp 0 (arrive)
+    constexpr int NBAR2 = 32 * (NTW + 2);     // named barrier 2: the same warps arrive, warp 4 waits (never the other way round)
+    constexpr bool kW4Tiles = (RBMAX == 13 && NTW == 6);
+    constexpr int NIT = (8 * (nlow + 1) + 31) / 32;
+    // warp 4: lower-stencil entries of the block entering the window at the NEXT step, fetched from the L2-resident
+    // scratch one step ahead so that the load latency is never on the step's critical path
+    double vnext[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j)
+      vnext[j] = (warp == 4 && RB < NBLK && lane + 32 * j < 8 * (nlow + 1)) ? __ldcg(stw + RB * 8 * (nlow + 1) + lane + 32 * j) : 0.0;
     for (int k = 0, kslot = 0; k < NBLK; ++k, kslot = (kslot + 1 == RB) ? 0 : kslot + 1) {
       PH(0)
       const int cur = k & 1;
@@ -268,11 +280,41 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
         dst[frag_pos(g, 2 * t)] = p0;
         dst[frag_pos(g, 2 * t + 1)] = p1;
       };
+      // W[I, J] -= Lp_I Lp_J^T for the tiles J = jlo .. jhi of block row I = k + offI (three at a time)
+      auto sweep_row = [&](int offI, int jlo, int jhi) {
+        if (offI > nl) return;
+        int sI = kslot + offI;
+        if (sI >= RB) sI -= RB;
+        const double a0 = -sLpT[t * LDP + 8 * sI + g], a1 = -sLpT[(4 + t) * LDP + 8 * sI + g];
+        double *rowp = sWf + (8 * sI + g) * LDWF + 2 * t;
+        for (int offJ = jlo; offJ <= jhi; offJ += 3) {
+          double2 c[3];
+          double b0[3], b1[3];
+          int sJ[3];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int oj = (offJ + u <= jhi) ? offJ + u : offJ;
+            sJ[u] = kslot + oj;
+            if (sJ[u] >= RB) sJ[u] -= RB;
+            c[u] = *reinterpret_cast<double2 *>(rowp + 8 * sJ[u]);
+            b0[u] = sLpT[t * LDP + 8 * sJ[u] + g];
+            b1[u] = sLpT[(4 + t) * LDP + 8 * sJ[u] + g];
+          }
+#pragma unroll
+          for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            if (offJ + u <= jhi) *reinterpret_cast<double2 *>(rowp + 8 * sJ[u]) = c[u];
+        }
+      };
       if (warp == 0) {
         if (nl >= 1) {
           panel_tile(1);
           __syncwarp();
           asm volatile("bar.arrive 1, %0;" ::"n"(NBAR) : "memory");   // tile 1 is in sLpT
+          if (kW4Tiles) asm volatile("bar.arrive 2, %0;" ::"n"(NBAR2) : "memory");
           int sI = kslot + 1;
           if (sI >= RB) sI -= RB;
           double *ct = sWf + (8 * sI + g) * LDWF + 8 * sI + 2 * t;
@@ -291,26 +333,73 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
           // tile 0 of the record: Linv in fragment order
           *reinterpret_cast<double2 *>(Ls + 2 * lane) = make_double2(Linv[g * 8 + t], Linv[g * 8 + 4 + t]);
           // Block row kslot (block k) is dead: only its diagonal tile was still needed, by the factorisation of the
-          // previous step, and nothing of it is read in this step.  Clear it, refill it with block k + RB from the
-          // staging buffer, and compute the entries of block k + RB + 1 for the next step -- mostly integer work.
+          // previous step, and nothing of it is read in this step.  Clear it and refill it with block k + RB from the
+          // stencil scratch.
           if (k + RB < NBLK) {
+            double v[NIT];
+#pragma unroll
+            for (int j = 0; j < NIT; ++j) {
+              v[j] = vnext[j];
+              vnext[j] = (k + RB + 1 < NBLK && lane + 32 * j < 8 * (nlow + 1))
+                             ? __ldcg(stw + (k + RB + 1) * 8 * (nlow + 1) + lane + 32 * j) : 0.0;
+            }
             for (int item = lane; item < 32 * RB; item += 32) {
               const int i = item & 7, q = item >> 3;
               *reinterpret_cast<double2 *>(sWf + (8 * kslot + i) * LDWF + 2 * q) = make_double2(0.0, 0.0);
             }
             __syncwarp();
-            scatter_block_row(k + RB, kslot, sStage + 128 * ((k + RB) & 1), lane, 32);
+#pragma unroll
+            for (int j = 0; j < NIT; ++j)
+              if (lane + 32 * j < 8 * (nlow + 1)) scatter_item(k + RB, kslot, lane + 32 * j, v[j]);
           }
-          if (k + RB + 1 < NBLK)
-            for (int item = lane; item < 8 * (nlow + 1); item += 32)
-              sStage[128 * ((k + RB + 1) & 1) + item] = stencil_item(k + RB + 1, item);
+          PH(8)
+          if (RBMAX == 13 && NTW == 6) {
+            if (nl >= 1) asm volatile("bar.sync 2, %0;" ::"n"(NBAR2) : "memory");   // the panel tiles are in sLpT
+            PH(9)
+            // diagonal tiles (r, r) of the rows 12 .. 7, three independent tiles at a time: W -= Lp_r Lp_r^T
+#pragma unroll 1
+            for (int r0 = RBMAX - 1; r0 >= RBMAX - 6; r0 -= 3) {
+              double *ct[3];
+              double2 c[3];
+              double a0[3], a1[3];
+#pragma unroll
+              for (int u = 0; u < 3; ++u) {
+                int sI = kslot + (r0 - u);
+                if (sI >= RB) sI -= RB;
+                ct[u] = sWf + (8 * sI + g) * LDWF + 8 * sI + 2 * t;
+                c[u] = *reinterpret_cast<double2 *>(ct[u]);
+                a0[u] = -sLpT[t * LDP + 8 * sI + g];
+                a1[u] = -sLpT[(4 + t) * LDP + 8 * sI + g];
+              }
+#pragma unroll
+              for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a0[u], -a0[u]);
+#pragma unroll
+              for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a1[u], -a1[u]);
+#pragma unroll
+              for (int u = 0; u < 3; ++u)
+                if (r0 - u <= nl) *reinterpret_cast<double2 *>(ct[u]) = c[u];
+            }
+          }
         }
       } else {
         const int wrank = warp - 1 - (warp >> 2);  // 0 .. NTW-1
         for (int off = 2 + wrank; off <= nl; off += NTW) panel_tile(off);
         PH(1)
+        if (nl >= 1 && kW4Tiles) {
+          __syncwarp();
+          asm volatile("bar.arrive 2, %0;" ::"n"(NBAR2) : "memory");
+        }
         if (nl >= 1) asm volatile("bar.sync 1, %0;" ::"n"(NBAR) : "memory");
         PH(3)
+        // Trailing tiles by block row: the pair (off, RBMAX - off) has RBMAX tiles for every off, so with RBMAX = 13 the six
+        // panel warps take one pair each (the diagonal tile (1, 1) belongs to warp 0).  A warp keeps the A fragments of
+        // its row and sweeps the columns three tiles at a time -- no tile table, half the operand loads.  The diagonal
+        // tiles of the long rows 7 .. 12 are left to warp 4 (sweep_row below), which has the fourth scheduler's tensor
+        // pipe to itself.
+        if (RBMAX == 13 && NTW == 6) {
+          sweep_row(1 + wrank, (wrank == 0) ? 2 : 1, 1 + wrank);
+          sweep_row(RBMAX - 1 - wrank, 1, RBMAX - 2 - wrank);
+        } else
         for (int tt = 1 + wrank; tt < ntile; tt += 3 * NTW) {
           double *ct[3];
           double2 c[3];
