@@ -41,6 +41,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   // have fewer interior nodes under them, consecutive rows would leave some warps with much less to gather)
   constexpr int RSTR = 2 * NTILE;
 
+  unsigned long long table_key = ~0ull;   // shape key (geom.h) of the patch the gather table was built for
   __shared__ int sNextWork;
   SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
     fetch_work_item(w, work_counter, &sNextWork);
@@ -48,6 +49,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     const Geom geo = make_geom(cP, pid);
     const int ncd = geo.Ncd, s = cP.s;
     const double *X = Xbuf + (size_t)w * lay.x_stride;
+    const bool rebuild = (shape_key(geo) != table_key);   // the table is integer geometry: per shape, not per patch
+    table_key = shape_key(geo);
     __syncthreads();
     PH_DECL
     load_coef(geo, d_coef, sCoef);
@@ -55,6 +58,7 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     // compacted per row by ballot. ----
     const int npc = cP.n + 1;
     const int nloc = (cP.dim == 3) ? npc * npc * npc : npc * npc;   // <= 27 (host guarantees)
+    if (rebuild)
     for (int idx = tid; idx < NC * 32; idx += NT) {
       const int row = idx >> 5, l = idx & 31;
       int e = -1;

@@ -110,6 +110,16 @@ SLOD_HD Geom make_geom(const Params &P, int pid) {
   return make_geom_at(P, c);
 }
 
+// Everything integer about a patch (index tables, boundary lists, column order) depends only on its per-axis extents,
+// the position of the centre cell and which sides lie on the domain boundary: patches with the same key share it.
+// The work lists are sorted by cost, so a persistent CTA sees long runs of equal keys and rebuilds its tables rarely.
+SLOD_HD unsigned long long shape_key(const Geom &g) {
+  unsigned long long k = 0;
+  for (int a = 0; a < 3; ++a)
+    k = (k << 20) | (unsigned long long)((g.m[a] << 10) | (g.cc[a] << 2) | (g.domlo[a] << 1) | g.domhi[a]);   // m, cc < 256
+  return k;
+}
+
 // list position (coarse column / spacedim) of patch cell k (relative coordinates)
 SLOD_HD int cell_to_col(const Params &P, const Geom &g, const int k[3]) {
   int t = (P.dim == 3) ? ((k[0] * g.m[1] + k[1]) * g.m[2] + k[2]) : (k[0] * g.m[1] + k[1]);

@@ -150,12 +150,15 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
   }
   for (int i = tid; i < 64; i += NT) sK[i] = cP.Kref[i];
 
+  unsigned long long table_key = ~0ull;   // shape key (geom.h) of the patch sRowPk / sDOff were built for
   __shared__ int sNextWork;
   SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
     fetch_work_item(w, work_counter, &sNextWork);
     const int pid = patch_ids[w];
     const Geom geo = make_geom(cP, pid);
     const int Ni = geo.Ni, bw = geo.bw, n = cP.n;
+    const bool rebuild = (shape_key(geo) != table_key);
+    table_key = shape_key(geo);
     const int NBLK = (Ni + 7) >> 3;
     int RB = (bw + 8 + 7) >> 3;
     if (RB > RBMAX) RB = RBMAX;  // host guarantees bw_max fits
@@ -166,6 +169,7 @@ k_patch_factor(const int *__restrict__ patch_ids, int n_work, const double *__re
     double *stw = stencil_ws + (size_t)blockIdx.x * lay.nip_max * (nlow + 1);
     __syncthreads();
     load_coef(geo, d_coef, sCoef);
+    if (rebuild)
     for (int r = tid; r < 8 * NBLK; r += NT) {
       int pk = 0;
       if (r < Ni) {
@@ -477,6 +481,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
   }
   __syncthreads();
   uint32_t rec_base = 0;   // records consumed so far by this CTA (ring position and barrier phases follow from it)
+  unsigned long long table_key = ~0ull;   // shape key (geom.h) the tables in shared memory were built for
 
   __shared__ int sNextWork;
   SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
@@ -489,7 +494,10 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
     if (RB > RBMAX) RB = RBMAX;
     double *X = Xbuf + (size_t)w * lay.x_stride;
     const double *rec = Lrec + (size_t)w * lay.rec_stride;
+    const bool rebuild = (shape_key(geo) != table_key);   // block-uniform: integer tables are per shape, not per patch
+    table_key = shape_key(geo);
     __syncthreads();   // the tables of the previous patch are dead
+    if (rebuild)
     for (int r = tid; r < 8 * NBLK; r += NT) {
       int pk = 0;
       if (r < Ni) {
@@ -499,6 +507,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       }
       sRowPk[r] = pk;
     }
+    if (rebuild)
     for (int col = tid; col < NC; col += NT) {
       int v = -1;
       if (col < ncd) {
@@ -537,6 +546,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
     }
     __syncthreads();
     // warps that do not take part in a step do not touch the ring: the producer arrives for them (below)
+    if (rebuild)
     for (int k = tid; k <= NBLK; k += NT) {
       int cnt = 0;
       for (int w2 = 0; w2 < NW; ++w2) cnt += (k < NBLK) ? (sKstart[w2] > k) : (sKstart[w2] >= NBLK);
