@@ -490,7 +490,8 @@ def main():
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "dram_traffic.json")   # per-launch DRAM bytes from the committed ncu capture
         if os.path.exists(tfile) and args.workload == DEFAULT_WORKLOAD and world == 1:
-            traffic = json.load(open(tfile)).get(kname.split(" ")[0])
+            tr = json.load(open(tfile))
+            traffic = tr.get(kname, tr.get(kname.split(" ")[0]))
         # FP64 peak of THIS device, measured now (same process, after the timed region) with the library's probe kernels
         peak, peak_src = FP64_PEAK_FALLBACK, "fallback constant (probe failed)"
         try:
