@@ -364,13 +364,13 @@ def main():
                     ctx.set_coefficient(f, w["r"], tb)
                 ctx.compute_basis()
                 ctx.assemble_coarse()            # enqueues; the basis read-back below overlaps the coarse kernels
-                ph, aph = ctx.all_basis(reuse=True)
+                ph, _ = ctx.all_basis(reuse=True, want_aphi=False)   # the host keeps phi and K; A*phi is an intermediate
                 rowptr, col, val = ctx.coarse_csr(reuse=True)
-                e2e_bytes[0] = val.nbytes + ph.nbytes + aph.nbytes
+                e2e_bytes[0] = val.nbytes + ph.nbytes
                 return float(val[0] + ph[0, 0, 0])
             e2e_bytes = [0]
             d2h = None
-            path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_all_basis+slod_get_coarse_csr"
+            path = "slod_set_coefficient+slod_compute_basis+slod_assemble_coarse+slod_get_all_basis(phi)+slod_get_coarse_csr"
         else:
             h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
             h_K = torch.empty(((p1 - p0) * s, ellw), dtype=torch.float64, pin_memory=True)
@@ -378,14 +378,17 @@ def main():
             def e2e_step():
                 for f, tb in enumerate(tables):
                     ctx.set_coefficient(f, w["r"], tb)
-                step(gather_K=False)
-                h_phi.copy_(phi[p0:p1], non_blocking=True)
-                h_K.copy_(K[p0 * s:p1 * s], non_blocking=True)
+                # the library copies the rank's rows of phi / K into the pinned buffers on its own stream as soon as they
+                # are final (phi while the all-gather and the coarse kernel still run); K is all-gathered on the devices
+                ctx.set_host_outputs(h_phi.data_ptr(), 0, h_K.data_ptr())
+                step(gather_K=True)
+                ctx.set_host_outputs(0, 0, 0)
                 torch.cuda.synchronize()
                 return float(h_K[0, 0] + h_phi[0, 0, 0])
             d2h = (p1 - p0) * s * (ellw + stride) * 8 * world
             path = ("per rank: slod_set_coefficient + slod_offline_distributed (NCCL all-gather of A*phi inside the library) + "
-                    "D2H of the rank's own rows of phi and K into pinned memory (row-distributed result, as an MPI host holds it)")
+                    "coarse rows + NCCL all-gather of K on the devices, D2H of the rank's own rows of phi and K into pinned memory "
+                    "overlapped by the library (row-distributed result, as an MPI host holds it)")
         e2e_step()
         barrier()
         t0 = time.perf_counter()

@@ -29,7 +29,7 @@ EXPORTS = [
     "slod_free_host", "slod_fine_size", "slod_coarse_rhs", "slod_coarse_solve", "slod_prolongate",
     "slod_fem_solve", "slod_fine_norms", "slod_synchronize", "slod_measure_fp64_peak", "slod_owned_range",
     "slod_comm_unique_id", "slod_comm_init", "slod_offline_distributed", "slod_save_state", "slod_load_state",
-    "slod_fine_norms_reference",
+    "slod_fine_norms_reference", "slod_set_host_outputs",
 ]
 
 
@@ -100,6 +100,7 @@ def load_library(path=None):
     lib.slod_fine_norms_reference.argtypes = [vp, P(dbl), P(dbl), P(dbl), P(dbl)]
     lib.slod_save_state.argtypes = [vp, C.c_char_p]
     lib.slod_load_state.argtypes = [vp, C.c_char_p]
+    lib.slod_set_host_outputs.argtypes = [vp, vp, vp, vp]
     lib.slod_owned_range.argtypes = [vp, C.c_int, C.c_int, P(i64), P(i64)]
     lib.slod_comm_unique_id.argtypes = [vp]
     lib.slod_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -276,11 +277,12 @@ class SlodContext:
         self._ck(self.lib.slod_basis_stride(self.h, C.byref(n)))
         return n.value
 
-    def all_basis(self, reuse=False):
+    def all_basis(self, reuse=False, want_aphi=True):
+        """(phi, A*phi) of all patches, [n_patches, spacedim, stride]; want_aphi=False skips the second array (None)."""
         shape = (self.n_patches, self.s, self.basis_stride)
         phi = self._out("phi", shape, reuse=reuse)
-        aphi = self._out("aphi", shape, reuse=reuse)
-        self._ck(self.lib.slod_get_all_basis(self.h, _dp(phi), _dp(aphi)))
+        aphi = self._out("aphi", shape, reuse=reuse) if want_aphi else None
+        self._ck(self.lib.slod_get_all_basis(self.h, _dp(phi), _dp(aphi) if want_aphi else None))
         return phi, aphi
 
     def assemble_coarse(self):
@@ -429,6 +431,12 @@ class SlodContext:
 
     def load_state(self, path):
         self._ck(self.lib.slod_load_state(self.h, os.fsencode(path)))
+
+    def set_host_outputs(self, h_phi=0, h_aphi=0, h_K=0):
+        """Host addresses (ints, 0 = none) for the rank's own rows of phi / A*phi / K: slod_offline_distributed copies them
+        on the library's own stream as soon as they are final, slod_synchronize waits for the copies."""
+        self._ck(self.lib.slod_set_host_outputs(self.h, C.c_void_p(h_phi or None), C.c_void_p(h_aphi or None),
+                                                C.c_void_p(h_K or None)))
 
     def synchronize(self):
         """Wait for the device-buffer calls above; raises SlodError (SLOD_ERR_NUMERIC) if a patch reported a status."""

@@ -108,6 +108,9 @@ struct slod_ctx {
   std::vector<slod_ctx *> subs;   // sub-handles of ranks 1 .. n_gpus-1 (owned)
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  double *h_out_phi = nullptr, *h_out_aphi = nullptr, *h_out_K = nullptr;   // slod_set_host_outputs
+  cudaEvent_t ev_out[2]{};       // basis rows ready | coarse rows ready
+  bool out_pending = false;
 };
 
 namespace {
@@ -1138,6 +1141,8 @@ void slod_destroy(slod_ctx *ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->chunk_ev) cudaEventDestroy(ev);
   if (ctx->ev_split) cudaEventDestroy(ctx->ev_split);
+  for (auto &ev : ctx->ev_out)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   delete ctx;
 }
@@ -1385,6 +1390,18 @@ int slod_offline_distributed(slod_ctx *ctx, double *d_phi, double *d_aphi, doubl
   const size_t per_patch = (size_t)ctx->P.s * ctx->P.NfMax;
   int rc = run_basis(ctx, b, e, d_phi, d_aphi, st);
   if (rc) return rc;
+  const bool host_out = ctx->h_out_phi || ctx->h_out_aphi || ctx->h_out_K;
+  if (host_out) {
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev_out)
+      if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ev_out[0], st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_out[0], 0));
+    const size_t off = (size_t)b * per_patch, cnt = (size_t)(e - b) * per_patch;
+    if (ctx->h_out_phi) CK(cudaMemcpyAsync(ctx->h_out_phi, d_phi + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (ctx->h_out_aphi) CK(cudaMemcpyAsync(ctx->h_out_aphi, d_aphi + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->out_pending = true;
+  }
   if (ctx->comm_world > 1) {
     rc = gather_blocks(ctx, d_aphi, per_patch, st);
     if (rc) return rc;
@@ -1392,8 +1409,24 @@ int slod_offline_distributed(slod_ctx *ctx, double *d_phi, double *d_aphi, doubl
   }
   rc = run_coarse(ctx, b, e, d_phi, d_aphi, d_K, st, false);
   if (rc) return rc;
+  if (host_out && ctx->h_out_K) {
+    const size_t per_k = (size_t)ctx->P.s * ctx->P.ell_width;
+    CK(cudaEventRecord(ctx->ev_out[1], st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_out[1], 0));
+    CK(cudaMemcpyAsync(ctx->h_out_K, d_K + (size_t)b * per_k, sizeof(double) * (size_t)(e - b) * per_k, cudaMemcpyDeviceToHost,
+                       ctx->copy_stream));
+  }
   if (ctx->comm_world > 1 && gather_K) rc = gather_blocks(ctx, d_K, (size_t)ctx->P.s * ctx->P.ell_width, st);
   return rc;
+}
+
+int slod_set_host_outputs(slod_ctx *ctx, double *h_phi, double *h_aphi, double *h_K) {
+  if (!ctx) return SLOD_ERR_INVALID;
+  NEED_DEVICE();
+  ctx->h_out_phi = h_phi;
+  ctx->h_out_aphi = h_aphi;
+  ctx->h_out_K = h_K;
+  return SLOD_OK;
 }
 
 int slod_synchronize(slod_ctx *ctx) {
@@ -1402,7 +1435,13 @@ int slod_synchronize(slod_ctx *ctx) {
   CK(cudaSetDevice(ctx->device));
   int rc = wait_basis(ctx);
   if (rc) return rc;
-  return finish_coarse_timing(ctx);
+  rc = finish_coarse_timing(ctx);
+  if (rc) return rc;
+  if (ctx->out_pending) {
+    ctx->out_pending = false;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+  }
+  return SLOD_OK;
 }
 
 int slod_get_basis(const slod_ctx *ctx, int64_t patch, int comp, double *phi, double *aphi) {

@@ -469,6 +469,10 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
   // groups evenly over the four schedulers (warp mod 4).
   const int grp = (NW == 16) ? (warp < 8 ? ((0x86543210u >> (4 * warp)) & 15) : ((0xCFED9BA7u >> (4 * (warp - 8))) & 15))
                              : warp;
+  // The ring producer is lane 0 of the warp that owns the LAST column group: with the z-major order its forward
+  // substitution starts at 3/4 of the rows (or never, on clipped patches where the group is padding), so it fills the
+  // ring ahead of the others instead of adding its bookkeeping to the critical path of a full-work warp.
+  const bool is_prod = (grp == NW - 1) && (lane == 0);
 
   if (tid == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -606,7 +610,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
         *sProgress = rec_base + issued;
       }
     };
-    if (tid == 0) top_up(NSTG - 1);
+    if (is_prod) top_up(NSTG - 1);
     // Wait for record r in its ring slot.  The parity test of an mbarrier only tells the current phase from the one
     // before it, and a warp that sat out the earlier uses of the slot may be several phases ahead of it: the record
     // must have been ISSUED (then the slot's barrier is in the phase of this record, or past it) before the test.
@@ -623,7 +627,9 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       if (off < RB && kstart + off < NBLK) rhs_tile(kstart + off, cr[off][0], cr[off][1]);
     }
     PHS_DECL(0, 5, NW - 1)
-    for (int k = (warp == 0) ? 0 : kstart; k < NBLK; ++k) {   // warp 0 (the producer) owns column group 0: kstart = 0
+    // the producer's idle steps: fill the ring as far as the consumers free it (the waits inside top_up pace it)
+    if (is_prod) top_up(min(kstart, NBLK) + NSTG - 1);
+    for (int k = kstart; k < NBLK; ++k) {
       PH(0)
       const uint32_t r = rec_base + k;
       const int slot = r % NSTG;
@@ -661,7 +667,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
           if (o4 + u < RBMAX && o4 + u <= nl) dmma884(cr[o4 + u][0], cr[o4 + u][1], a[u].y, yb1);
       }
       // the producer refills the ring while the tensor pipe works through the instructions just issued
-      if (tid == 0) top_up(k + NSTG - 1);
+      if (is_prod) top_up(k + NSTG - 1);
       PH(1)
       __syncwarp();
       if (lane == 0) mbar_arrive(sEmpty + slot);
@@ -684,8 +690,10 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
       return (k >= kstart) ? *reinterpret_cast<const double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t)
                            : make_double2(0.0, 0.0);
     };
-    if (kstart >= NBLK && warp != 0) {
-      // padding columns only: X = 0 (finite values for the consumers), no arithmetic, no part in the ring
+    if (kstart >= NBLK) {
+      // padding columns only: X = 0 (finite values for the consumers), no arithmetic, no part in the ring -- but the
+      // producer keeps feeding it
+      if (is_prod) top_up(total);
       for (int k = 0; k < NBLK; ++k)
         *reinterpret_cast<double2 *>(X + (size_t)(8 * k + g) * lay.ldx + 8 * grp + 2 * t) = make_double2(0.0, 0.0);
       rec_base += (uint32_t)total;
@@ -722,7 +730,7 @@ k_patch_trisolve(const int *__restrict__ patch_ids, int n_work, const double *__
           dmma1688(c[off & 1][0], c[off & 1][1], c[off & 1][2], c[off & 1][3], a0, a1, a2, a3, xr[off][0], xr[off][1]);
         }
       }
-      if (tid == 0) top_up(i + NSTG - 3);   // slots of the pair before the previous one: warp 0 never waits for a straggler
+      if (is_prod) top_up(i + NSTG - 3);   // slots of the pair before the previous one: the producer never waits for a straggler
       PH(6)
       const double c0 = c[0][0] + c[1][0], c1 = c[0][1] + c[1][1];
       double p0 = c[0][2] + c[1][2], p1 = c[0][3] + c[1][3];

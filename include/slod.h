@@ -227,6 +227,11 @@ int slod_comm_init(slod_ctx *ctx, int rank, int world, const void *id128);
  * Everything is enqueued on `stream`; slod_synchronize() is the synchronisation point. */
 int slod_offline_distributed(slod_ctx *ctx, double *d_phi, double *d_A_phi, double *d_K, int gather_phi, int gather_K,
                              void *stream);
+/* Host destinations for the rank's OWN rows ([rows of slod_owned_range][spacedim][stride] for phi / A*phi,
+ * [rows * spacedim][ell_width] for K; page-locked memory recommended; any pointer may be NULL).  When set,
+ * slod_offline_distributed copies the rows on the handle's own stream as soon as the producing kernels are through --
+ * phi while the A*phi all-gather and the coarse-matrix kernel still run -- and slod_synchronize waits for the copies. */
+int slod_set_host_outputs(slod_ctx *ctx, double *h_phi_rows, double *h_A_phi_rows, double *h_K_rows);
 /* convert a host copy of the block-ELL matrix into CSR (same contract as slod_get_coarse_csr) */
 int slod_ell_to_csr(const slod_ctx *ctx, const double *h_K, int64_t *rowptr, int64_t *col, double *val,
                     int64_t *n_rows, int64_t *nnz);

@@ -45,9 +45,15 @@ def test_no_cpu_fallback(lib):
 
 def test_parameter_validation(lib):
     for kw in (dict(dim=1), dict(dim=2, spacedim=2), dict(dim=3, spacedim=3, problem=1), dict(dim=2, n_subdivisions=3),
-               dict(dim=2, oversampling=-1)):
+               dict(dim=2, oversampling=-1), dict(dim=2, n_gpus=-1), dict(dim=2, n_gpus=2)):   # n_gpus > 1 needs devices
         with pytest.raises(pkg.SlodError):
             pkg.SlodContext(device=-2, **kw)
+    # a patch without interior fine dofs (one-cell patches with one subdivision) is refused, not computed
+    for kw in (dict(dim=2, n_global_refinements=2, n_subdivisions=1, oversampling=0),
+               dict(dim=3, n_global_refinements=0, n_subdivisions=1, oversampling=1)):
+        with pytest.raises(pkg.SlodError) as e:
+            pkg.SlodContext(device=-2, **kw)
+        assert e.value.code == 2 and "interior" in str(e.value)
 
 
 @pytest.mark.parametrize("dim,s,ref,n,ell", [(2, 1, 3, 2, 1), (2, 1, 4, 2, 2), (2, 2, 3, 2, 1), (2, 1, 2, 4, 1),

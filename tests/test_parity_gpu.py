@@ -242,3 +242,31 @@ def test_multi_chunk_loop(case, monkeypatch):
     assert np.array_equal(p, p_ref) and np.array_equal(a, a_ref)
     assert np.array_equal(ctx.coarse_csr()[2], k_ref)
     assert ctx.timings()[0] > 0
+
+
+def test_offline_distributed_single_rank_with_host_outputs():
+    """slod_offline_distributed on a communicator-less handle (world 1) = basis + coarse rows of all patches, enqueued;
+    slod_set_host_outputs makes the library copy phi / A phi / K rows to host memory on its own stream; everything is
+    bit-identical to the host-buffer path."""
+    import torch
+    ctx, _ = build_pair(dim=2, s=1, ref=4, n=2, ell=2, seed=9)
+    ctx.compute_basis()
+    ctx.assemble_coarse()
+    p_ref, a_ref = (x.copy() for x in ctx.all_basis())
+    k_ref = ctx.coarse_csr()[2].copy()
+    n, stride, ellw = ctx.n_patches, ctx.basis_stride, ctx.ell_width
+    assert ctx.owned_range(0, 1) == (0, n)
+    phi = torch.zeros((n, 1, stride), dtype=torch.float64, device="cuda")
+    aphi = torch.zeros_like(phi)
+    K = torch.zeros((n, ellw), dtype=torch.float64, device="cuda")
+    h_phi = torch.empty((n, 1, stride), dtype=torch.float64, pin_memory=True)
+    h_aphi = torch.empty_like(h_phi, pin_memory=True)
+    h_K = torch.empty((n, ellw), dtype=torch.float64, pin_memory=True)
+    ctx.set_host_outputs(h_phi.data_ptr(), h_aphi.data_ptr(), h_K.data_ptr())
+    ctx.offline_distributed(phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), gather_phi=True, gather_K=True)
+    ctx.synchronize()
+    ctx.set_host_outputs(0, 0, 0)
+    assert np.array_equal(h_phi.numpy(), p_ref) and np.array_equal(h_aphi.numpy(), a_ref)
+    torch.cuda.synchronize()
+    assert np.array_equal(phi.cpu().numpy(), p_ref)
+    assert np.array_equal(ctx.ell_to_csr(h_K.numpy())[2], k_ref)
