@@ -122,21 +122,27 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       __syncthreads();
       int badpiv = 0;
       const int nblk = (ncd + 7) >> 3;
-      double *sPinv = sPivRow;       // [64] current Pinv (row-major), the pivot vectors are not needed any more
-      double *sLi = sPivRow + 64;    // [64] scratch: L^{-1}
-      auto invert_pivot = [&](int K) {  // warp 0: Pinv = (L^{-1})^T L^{-1} of block K
-        const double2 pv = *reinterpret_cast<const double2 *>(sM + (8 * K + g) * LDM + 8 * K + 2 * t);
+      double *sPinvB = sT;           // [2][64] Pinv of step K in buffer K & 1 (row-major); sT is free until the W tiles
+      double *sLi = sT + 128;        // [64] scratch: L^{-1}
+      auto invert_pivot = [&](double2 pv, double *Pinv) {  // one warp: Pinv = (L^{-1})^T L^{-1} of the tile held in C layout
         badpiv |= chol8_inv(pv.x, pv.y, lane, sLi);
         double p0 = 0.0, p1 = 0.0;
         const double f0 = sLi[t * 8 + g], f1 = sLi[(4 + t) * 8 + g];  // A[m][k] = Li[k][m] and B[k][n] = Li[k][n]
         dmma884(p0, p1, f0, f0);
         dmma884(p0, p1, f1, f1);
-        *reinterpret_cast<double2 *>(sPinv + g * 8 + 2 * t) = make_double2(p0, p1);
+        *reinterpret_cast<double2 *>(Pinv + g * 8 + 2 * t) = make_double2(p0, p1);
       };
-      if (warp == 0) invert_pivot(0);
+      if (warp == 0) invert_pivot(*reinterpret_cast<const double2 *>(sM + g * LDM + 2 * t), sPinvB);
       __syncthreads();
+      // Two barriers per step.  Warp K owns the pivot row and has no tile to update in step K: it looks ahead instead --
+      // it forms the final value of the next pivot block (K+1, K+1) in registers (the same two DMMAs warp K+1 applies to
+      // that tile, so the bits agree) and inverts it into the other Pinv buffer while the others sweep their rows.
       for (int K = 0; K < nblk; ++K) {
         PH(2)
+        const double *sPinv = sPinvB + (K & 1) * 64;
+        double2 la_c = make_double2(0.0, 0.0);
+        double la_a0 = 0.0, la_a1 = 0.0;
+        const bool lookahead = (warp == K) && (K + 1 < nblk);
         // ---- R_KJ = Pinv M_KJ, in place; NTILE - 1 tiles over the warps (warp J handles tile J) ----
         if (warp != K && warp < nblk) {
           const int J = warp;
@@ -147,11 +153,16 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           dmma884(r0_, r1_, sPinv[g * 8 + 4 + t], b1);
           __syncwarp();
           *reinterpret_cast<double2 *>(ct) = make_double2(r0_, r1_);
+        } else if (lookahead) {   // block row K + 1 is not touched in this phase
+          const double *rowp = sM + (8 * (K + 1) + g) * LDM;
+          la_c = *reinterpret_cast<const double2 *>(rowp + 8 * (K + 1) + 2 * t);
+          la_a0 = -rowp[8 * K + t];
+          la_a1 = -rowp[8 * K + 4 + t];
         }
         __syncthreads();
         PH(9)
-        // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments, sweeps J three tiles at a time ----
         if (warp != K && warp < nblk) {
+          // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments, sweeps J three tiles at a time ----
           const int I = warp;
           const double a0 = -sM[(8 * I + g) * LDM + 8 * K + t], a1 = -sM[(8 * I + g) * LDM + 8 * K + 4 + t];
           for (int J0 = 0; J0 < nblk; J0 += 3) {
@@ -175,29 +186,24 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
               if (J < nblk && J != K) *reinterpret_cast<double2 *>(sM + (8 * I + g) * LDM + 8 * J + 2 * t) = c[u];
             }
           }
+          // ---- column block: M_IK = -M_IK Pinv.  Only warp I reads or writes tile (I, K) in this step, and the mma is
+          // warp synchronous (every lane has loaded its fragment before any lane stores) ----
+          double2 newcol = make_double2(0.0, 0.0);
+          dmma884(newcol.x, newcol.y, a0, sPinv[t * 8 + g]);
+          dmma884(newcol.x, newcol.y, a1, sPinv[(4 + t) * 8 + g]);
+          *reinterpret_cast<double2 *>(sM + (8 * I + g) * LDM + 8 * K + 2 * t) = newcol;
+        } else if (warp == K) {
+          if (lookahead) {
+            dmma884(la_c.x, la_c.y, la_a0, sM[(8 * K + t) * LDM + 8 * (K + 1) + g]);
+            dmma884(la_c.x, la_c.y, la_a1, sM[(8 * K + 4 + t) * LDM + 8 * (K + 1) + g]);
+            invert_pivot(la_c, sPinvB + ((K + 1) & 1) * 64);
+          }
+          // M_KK = Pinv (nobody reads tile (K, K) in this step)
+          *reinterpret_cast<double2 *>(sM + (8 * K + g) * LDM + 8 * K + 2 * t) =
+              *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
         }
         __syncthreads();
         PH(10)
-        // ---- column block: M_IK = -M_IK Pinv (warp I), M_KK = Pinv (warp K); warp 0 inverts the next pivot first ----
-        double2 newcol = make_double2(0.0, 0.0);
-        if (warp < nblk) {
-          if (warp == K) {
-            newcol = *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
-          } else {
-            const int I = warp;
-            const double a0 = -sM[(8 * I + g) * LDM + 8 * K + t], a1 = -sM[(8 * I + g) * LDM + 8 * K + 4 + t];
-            dmma884(newcol.x, newcol.y, a0, sPinv[t * 8 + g]);
-            dmma884(newcol.x, newcol.y, a1, sPinv[(4 + t) * 8 + g]);
-          }
-        }
-        __syncthreads();   // every warp has read Pinv(K) and its old column tile
-        if (warp < nblk) *reinterpret_cast<double2 *>(sM + (8 * warp + g) * LDM + 8 * K + 2 * t) = newcol;
-        if (warp == 0 && K + 1 < nblk) {
-          // block (K+1, K+1) is final since the update above; warp 0's own column tile (row 0) is not part of it
-          invert_pivot(K + 1);
-        }
-        __syncthreads();
-        PH(11)
       }
       if (badpiv && lane == 0) atomicOr(&status[pid], 2);
       double *Mo = Minv_out + (size_t)w * lay.m_stride;
