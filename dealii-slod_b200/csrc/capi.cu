@@ -132,6 +132,48 @@ int fail(const slod_ctx *c, int code, const std::string &msg) {
   } while (0)
 
 
+// ---- the kernels' parameter block ----------------------------------------------------------------------------------
+// The kernels read one __constant__ Params block per device.  A call that launches kernels binds the handle's block for
+// its scope: the device's binding mutex is held (calls of different handles on one device enqueue one after the other,
+// never interleaved), the block is uploaded on the call's stream only if the resident bytes differ, and such an upload
+// first waits for the last kernels that were enqueued under the previous contents (an event recorded when a binding
+// ends).  Several handles with different parameters can therefore share a device and compute from different host
+// threads and streams; handles with equal parameters never cause an upload.
+struct DeviceParams {
+  std::recursive_mutex mu;   // recursive: an entry point may call another one that binds again
+  bool valid = false;
+  Params resident;
+  cudaEvent_t busy = nullptr;
+};
+DeviceParams &device_params(int device) {
+  static DeviceParams table[64];
+  return table[(device >= 0 && device < 64) ? device : 0];
+}
+struct ParamBinding {
+  DeviceParams &dp;
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+  ParamBinding(const slod_ctx *ctx, cudaStream_t stream) : dp(device_params(ctx->device)), st(stream) {
+    dp.mu.lock();
+    if (dp.valid && std::memcmp(&dp.resident, &ctx->P, sizeof(Params)) == 0) return;
+    dp.valid = false;
+    if (dp.busy && (err = cudaStreamWaitEvent(st, dp.busy, 0)) != cudaSuccess) return;
+    if ((err = upload_params(ctx->P, st)) != cudaSuccess) return;
+    std::memcpy(&dp.resident, &ctx->P, sizeof(Params));
+    dp.valid = true;
+  }
+  ~ParamBinding() {
+    if (!dp.busy) cudaEventCreateWithFlags(&dp.busy, cudaEventDisableTiming);
+    if (dp.busy) cudaEventRecord(dp.busy, st);
+    dp.mu.unlock();
+  }
+  ParamBinding(const ParamBinding &) = delete;
+  ParamBinding &operator=(const ParamBinding &) = delete;
+};
+#define BIND_PARAMS(stream)            \
+  ParamBinding bound__(ctx, (stream)); \
+  CK(bound__.err)
+
 // ---- NCCL, loaded on demand ---------------------------------------------------------------------------------------
 struct NcclApi {
   void *lib = nullptr;
@@ -510,7 +552,7 @@ int run_basis(slod_ctx *ctx, int64_t p0, int64_t p1, double *d_phi, double *d_ap
   if (rc) return rc;
   rc = ensure_workspace(ctx, p1 - p0);
   if (rc) return rc;
-  CK(upload_params(P));
+  BIND_PARAMS(st);
   // work order: largest patches first (integer geometry: cached per range, on the host and on the device)
   if (ctx->ids_p0 != p0 || ctx->ids_p1 != p1) {
     std::vector<int> order((size_t)(p1 - p0));
@@ -638,7 +680,7 @@ int run_coarse(slod_ctx *ctx, int64_t p0, int64_t p1, const double *d_phi, const
                cudaStream_t st, bool wait = true) {
   if (p0 < 0 || p1 > ctx->n_patches || p0 > p1) return fail(ctx, SLOD_ERR_INVALID, "bad patch range");
   if (p0 == p1) return SLOD_OK;
-  CK(upload_params(ctx->P));
+  BIND_PARAMS(st);
   CK(cudaEventRecord(ctx->ev[5], st));
   if (ctx->coarse_nu > 0)
     CK(launch_coarse_blocked(ctx->P.dim, ctx->P.s, ctx->n_sm, ctx->smem_coarse_blk, st, (int)p0, (int)p1, d_phi, d_aphi,
@@ -1595,7 +1637,7 @@ int slod_coarse_rhs(slod_ctx *ctx, const double *f_fine, double *rhs_coarse) {
   if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
   if (!f_fine || !rhs_coarse) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
   CK(cudaSetDevice(ctx->device));
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   int64_t n_fine = 0;
   slod_fine_size(ctx, &n_fine);
   const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
@@ -1620,7 +1662,7 @@ int slod_coarse_solve(slod_ctx *ctx, const double *rhs_coarse, double *u_coarse,
   if (max_steps < 0 || !(tolerance >= 0.0) || !(reduction >= 0.0))
     return fail(ctx, SLOD_ERR_INVALID, "solver control: max_steps, tolerance and reduction must be non-negative");
   CK(cudaSetDevice(ctx->device));
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   const int nrows = (int)(ctx->n_patches * ctx->P.s);
   double *d_b = nullptr, *d_x = nullptr, *d_work = nullptr;
   int rc = online_scratch(ctx, nullptr, nullptr, &d_b, &d_x, &d_work);
@@ -1655,7 +1697,7 @@ int slod_prolongate(slod_ctx *ctx, const double *u_coarse, double *u_fine) {
   if (!ctx->basis_done) return fail(ctx, SLOD_ERR_STATE, "slod_compute_basis has not run");
   if (!u_coarse || !u_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
   CK(cudaSetDevice(ctx->device));
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   int64_t n_fine = 0;
   slod_fine_size(ctx, &n_fine);
   const size_t nc = (size_t)ctx->n_patches * ctx->P.s;
@@ -1683,7 +1725,7 @@ int slod_fem_solve(slod_ctx *ctx, const double *f_fine, double *u_fine, int32_t 
   CK(cudaSetDevice(ctx->device));
   int rc = prepare_coefficients(ctx);
   if (rc) return rc;
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   const Params &P = ctx->P;
   int64_t n_fine = 0;
   slod_fine_size(ctx, &n_fine);
@@ -1735,7 +1777,7 @@ int slod_fine_norms(slod_ctx *ctx, const double *v_fine, double *l2, double *h1_
   CK(cudaSetDevice(ctx->device));
   int rc = prepare_coefficients(ctx);
   if (rc) return rc;
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   int64_t n_fine = 0;
   slod_fine_size(ctx, &n_fine);
   const long long n_nodes = n_fine / ctx->P.s;
@@ -1792,7 +1834,7 @@ int slod_fine_norms_reference(slod_ctx *ctx, const double *v_fine, double *l2, d
   NEED_DEVICE();
   if (!v_fine) return fail(ctx, SLOD_ERR_INVALID, "null buffer");
   CK(cudaSetDevice(ctx->device));
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   int64_t n_fine = 0;
   slod_fine_size(ctx, &n_fine);
   const int nq = 2 * (ctx->P.n + 1);   // QGauss((fe.degree + 1) * 2), degree of FE_Q_iso_Q1(n) = n
@@ -1964,7 +2006,7 @@ int slod_debug_patch_stages(slod_ctx *ctx, int64_t patch, double *X, double *Min
   if (rc) return rc;
   rc = ensure_workspace(ctx, 1);
   if (rc) return rc;
-  CK(upload_params(ctx->P));
+  BIND_PARAMS((cudaStream_t)0);
   ctx->ids_p0 = ctx->ids_p1 = -1;   // the device work list is overwritten below
   const int id = (int)patch;
   CK(cudaMemcpy(ctx->d_ids, &id, sizeof(int), cudaMemcpyHostToDevice));

@@ -28,12 +28,10 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
   constexpr int TW = NTILE / 2;   // register tile: 4 rows x TW columns per thread; thread tx owns columns tx + 16 j
                                   // (interleaved: the pivot-row reads of a half warp are 16 consecutive doubles)
   extern __shared__ double smem[];
-  double *sCoef = smem;
-  double *sM = sCoef + lay.coef_doubles;  // [NC][LDM]   M^{-1} for the mma B operand
-  double *sT = sM + NC * LDM;             // [kDTB][LDM] W tile, then BD tile
-  double *sPivRow = sT + kDTB * LDM;      // [2][NC]
-  double *sPivCol = sPivRow + 2 * NC;     // [2][NC]
-  int *sMList = (int *)(sPivCol + 2 * NC);  // [NC][32] X rows under each coarse row: (xrow << 2 | log2 weight) or -1
+  double *sM = smem;                      // [NC][LDM]   M, then M^{-1} for the mma B operand
+  double *sT = sM + NC * LDM;             // [kDTB][LDM] W tile, then BD tile (even tiles); scratch of the Gauss-Jordan
+  double *sT2 = sT + kDTB * LDM;          // [kDTB][LDM] the same for the odd tiles
+  int *sMList = (int *)(sT2 + kDTB * LDM);  // [NC][32] X rows under each coarse row: (xrow << 2 | log2 weight) or -1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ty = tid >> 4, tx = tid & 15;
@@ -43,17 +41,40 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
 
   unsigned long long table_key = ~0ull;   // shape key (geom.h) of the patch the gather table was built for
   __shared__ int sNextWork;
+  // staged accumulation of M (3-D scalar problems): two node layers of X in flight as bulk copies
+  constexpr int KZ = 5;                     // coarse cells per axis of a patch the staged path handles (l <= 2)
+  constexpr size_t kStageCap = (size_t)NC * LDM + 2 * (size_t)kDTB * LDM + (NC * 32) / 2;   // doubles from sM on
+  __shared__ __align__(8) uint64_t sBar[2];
+  uint32_t bar_phase = 0;                   // bit b: phase of sBar[b] the next wait expects (uniform over the CTA)
+  if (tid == 0) {
+    mbar_init(&sBar[0], 1);
+    mbar_init(&sBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   SLOD_WORK_LOOP(w, n_work, work_counter, sNextWork) {
     fetch_work_item(w, work_counter, &sNextWork);
     const int pid = patch_ids[w];
     const Geom geo = make_geom(cP, pid);
     const int ncd = geo.Ncd, s = cP.s;
     const double *X = Xbuf + (size_t)w * lay.x_stride;
-    const bool rebuild = (shape_key(geo) != table_key);   // the table is integer geometry: per shape, not per patch
-    table_key = shape_key(geo);
+    const size_t layer_doubles = (size_t)geo.q[0] * geo.q[1] * lay.ldx;
+    const bool staged = (TW % 2 == 0) && cP.dim == 3 && s == 1 && geo.m[0] * geo.m[1] <= NT / 16 && geo.m[2] <= KZ &&
+                        2 * layer_doubles <= kStageCap && (smem_u32(sM) & 15u) == 0 && lay.ldx >= NC;
+    const bool rebuild = !staged && (shape_key(geo) != table_key);   // the table is integer geometry: per shape, not per patch
+    table_key = staged ? ~0ull : shape_key(geo);                     // the staging buffers overlay the table
     __syncthreads();
     PH_DECL
-    load_coef(geo, d_coef, sCoef);
+    if (staged && tid == 0) {
+      // the previous patch used the region through the generic proxy (everybody is past the barrier above)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(layer_doubles * sizeof(double));
+      mbar_expect_tx(&sBar[0], bytes);
+      bulk_g2s(sM, X, bytes, &sBar[0]);
+      if (geo.q[2] > 1) {
+        mbar_expect_tx(&sBar[1], bytes);
+        bulk_g2s(sM + layer_doubles, X + layer_doubles, bytes, &sBar[1]);
+      }
+    }
     // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row; one (row, local node) pair per thread,
     // compacted per row by ballot. ----
     const int npc = cP.n + 1;
@@ -84,6 +105,82 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     __syncthreads();
 
     PH(0)
+    if (staged) {
+      // ---- M = P_i^T X / H^d, X read exactly once: the interior rows of one node layer (z fixed) are contiguous in X
+      // and arrive as one bulk copy (two layers in flight).  Thread = (cell column (kx, ky), 8 coarse columns); per
+      // layer it adds the (at most 3 x 3) interior nodes of its cell column with the x-y projection weights and hands
+      // the sum to the (at most two) cells of the column that contain the layer. ----
+      const int cxy = tid >> 4, tx2 = 2 * (tid & 15);
+      const int kx = cxy / geo.m[1], ky = cxy - kx * geo.m[1];
+      const bool active = cxy < geo.m[0] * geo.m[1];
+      const int nn = cP.n, q0 = geo.q[0];
+      double acc[KZ][TW];
+#pragma unroll
+      for (int kz = 0; kz < KZ; ++kz)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) acc[kz][j] = 0.0;
+      const uint32_t bytes = (uint32_t)(layer_doubles * sizeof(double));
+      for (int zi = 0; zi < geo.q[2]; ++zi) {
+        const int b = zi & 1;
+        mbar_wait(&sBar[b], (bar_phase >> b) & 1u);
+        bar_phase ^= 1u << b;
+        const double *L = sM + (size_t)b * layer_doubles;
+        double t2[TW];
+#pragma unroll
+        for (int j = 0; j < TW; ++j) t2[j] = 0.0;
+        if (active) {
+          for (int ty_ = 0; ty_ <= nn; ++ty_) {
+            const int ay = nn * ky + ty_;
+            if (ay < 1 || ay > geo.p[1] - 2) continue;
+            const double wy = (ty_ != 0 && ty_ != nn) ? 2.0 : 1.0;
+            for (int tx_ = 0; tx_ <= nn; ++tx_) {
+              const int ax = nn * kx + tx_;
+              if (ax < 1 || ax > geo.p[0] - 2) continue;
+              const double wxy = (tx_ != 0 && tx_ != nn) ? 2.0 * wy : wy;
+              const double2 *src = reinterpret_cast<const double2 *>(L + (size_t)((ay - 1) * q0 + (ax - 1)) * lay.ldx + tx2);
+#pragma unroll
+              for (int j = 0; j < TW / 2; ++j) {
+                const double2 v = src[16 * j];
+                t2[2 * j] += wxy * v.x;
+                t2[2 * j + 1] += wxy * v.y;
+              }
+            }
+          }
+          const int az = zi + 1;
+#pragma unroll
+          for (int kz = 0; kz < KZ; ++kz)
+            if (az >= nn * kz && az <= nn * kz + nn) {
+              const double wz = (az != nn * kz && az != nn * kz + nn) ? 2.0 : 1.0;
+#pragma unroll
+              for (int j = 0; j < TW; ++j) acc[kz][j] += wz * t2[j];
+            }
+        }
+        __syncthreads();   // everybody is done with buffer b
+        if (tid == 0 && zi + 2 < geo.q[2]) {
+          mbar_expect_tx(&sBar[b], bytes);
+          bulk_g2s(sM + (size_t)b * layer_doubles, X + (size_t)(zi + 2) * layer_doubles, bytes, &sBar[b]);
+        }
+      }
+      // all copies have landed and been consumed: M replaces the staging buffers (padding rows/cols: identity)
+      const double scale = cP.pw / cP.Hd;
+      if (active) {
+#pragma unroll
+        for (int kz = 0; kz < KZ; ++kz)
+          if (kz < geo.m[2]) {
+            const int kc[3] = {kx, ky, kz};
+            const int row = lay.zmajor ? zcell_to_col(geo, kc) : cell_to_col(cP, geo, kc);
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+              const int col = tx2 + 32 * (j >> 1) + (j & 1);
+              sM[row * LDM + col] = (col < ncd) ? acc[kz][j] * scale : 0.0;
+            }
+          }
+      }
+      for (int idx = tid; idx < (NC - ncd) * NC; idx += NT) {
+        const int row = ncd + idx / NC, col = idx % NC;
+        sM[row * LDM + col] = (row == col) ? 1.0 : 0.0;
+      }
+    } else {
     // ---- M = P_i^T X / H^d into the register tile (padding rows/cols: identity) ----
     double m[4][TW];
     {
@@ -108,17 +205,17 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TW; ++j) sM[(ty + RSTR * i) * LDM + tx + 16 * j] = m[i][j];
+    }
     PH(1)
     // ---- M^{-1}: blocked Gauss-Jordan (8 x 8 pivot blocks, no pivoting: M is SPD) with DMMA tile updates in
     // shared memory; replaces FullMatrix::gauss_jordan (source/LOD.cc:553).  Step K:
     //   Pinv = M_KK^{-1};  R_KJ = Pinv M_KJ;  M_IJ -= M_IK R_KJ (I, J != K);  M_IK = -M_IK Pinv;  M_KJ = R_KJ;  M_KK = Pinv.
-    // Warp w owns block row I = w.  The next pivot block is inverted by warp 0 while the others finish the column
-    // block, so a step costs three barriers.
+    // Warp w owns block row I = w; the pivot block of the next step is inverted one step ahead (below).
     {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < TW; ++j) sM[(ty + RSTR * i) * LDM + tx + 16 * j] = m[i][j];
       __syncthreads();
       int badpiv = 0;
       const int nblk = (ncd + 7) >> 3;
@@ -238,23 +335,26 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     const int ksteps = (ncd + 3) >> 2;
     const int I1 = warp % (NTILE / 2), I2 = NTILE - 1 - I1;
     const int e_base = (warp / (NTILE / 2)) * NGA;   // first entry of this warp in the pair's list of NTILE + 1 tiles
-    // W = S_b X - P_b comes from k_patch_flux, zero padded to whole tiles; a thread moves 8 doubles of each tile
-    // (NT * 8 = 32 * NC) and holds the next tile in registers while the tensor phases of the current one run.
+    // W = S_b X - P_b comes from k_patch_flux, zero padded to whole tiles.  The tiles alternate between two buffers:
+    // a thread moves 64 bytes of a tile with cp.async (NT * 8 = 32 * NC doubles), tile i + 1 is in flight while the
+    // tensor phases of tile i run, and BD replaces W in the tile's own buffer.
     const double *Wp = Wbuf + (size_t)w * lay.w_stride;
     const int wrow = tid / (NC / 8), wcol = 8 * (tid % (NC / 8));
-    double2 wreg[4];
-    auto load_w = [&](int t0) {
-      const double2 *src = reinterpret_cast<const double2 *>(Wp + (size_t)(t0 + wrow) * NC + wcol);
+    auto issue_w = [&](int t0, double *buf) {
+      const double *src = Wp + (size_t)(t0 + wrow) * NC + wcol;
+      const uint32_t dst = smem_u32(buf + wrow * LDM + wcol);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) wreg[q] = src[q];
+      for (int q = 0; q < 4; ++q)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * q), "l"(src + 2 * q) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (nbd > 0) load_w(0);
-    for (int t0 = 0; t0 < nbd; t0 += kDTB) {
+    if (nbd > 0) issue_w(0, sT);
+    for (int t0 = 0, it = 0; t0 < nbd; t0 += kDTB, ++it) {
       PH(3)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) *reinterpret_cast<double2 *>(sT + wrow * LDM + wcol + 2 * q) = wreg[q];
-      if (t0 + kDTB < nbd) load_w(t0 + kDTB);
-      __syncthreads();
+      double *sW = (it & 1) ? sT2 : sT;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // tile `it` is complete and visible; nobody reads the other buffer (Gram of tile it - 1) any more
+      if (t0 + kDTB < nbd) issue_w(t0 + kDTB, (it & 1) ? sT : sT2);
       PH(5)
       // BD tile = W tile * Minv : warp owns 8 columns, 4 row tiles
       double bd[4][2];
@@ -263,18 +363,18 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       for (int kk = 0; kk < ksteps; ++kk) {
         const double bf = sM[(4 * kk + t) * LDM + 8 * warp + g];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dmma884(bd[i][0], bd[i][1], sT[(8 * i + g) * LDM + 4 * kk + t], bf);
+        for (int i = 0; i < 4; ++i) dmma884(bd[i][0], bd[i][1], sW[(8 * i + g) * LDM + 4 * kk + t], bf);
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<double2 *>(sT + (8 * i + g) * LDM + 8 * warp + 2 * t) = make_double2(bd[i][0], bd[i][1]);
+        *reinterpret_cast<double2 *>(sW + (8 * i + g) * LDM + 8 * warp + 2 * t) = make_double2(bd[i][0], bd[i][1]);
       __syncthreads();
       PH(6)
       // G += BD^T BD on the owned lower-triangle tiles
 #pragma unroll
       for (int jj = 0; jj < kDTB / 4; ++jj) {
-        const double *rowp = sT + (4 * jj + t) * LDM + g;
+        const double *rowp = sW + (4 * jj + t) * LDM + g;
         const double a1 = rowp[8 * I1], a2 = rowp[8 * I2];
 #pragma unroll
         for (int el = 0; el < NGA; ++el) {
@@ -285,7 +385,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
           dmma884(gacc[el][0], gacc[el][1], first ? a1 : a2, rowp[8 * J]);
         }
       }
-      __syncthreads();   // the next tile overwrites sT
       PH(7)
     }
     {

@@ -23,7 +23,9 @@ namespace slod {
 
 __constant__ Params cP;
 
-cudaError_t upload_params(const Params &p) { return cudaMemcpyToSymbol(cP, &p, sizeof(Params)); }
+cudaError_t upload_params(const Params &p, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(cP, &p, sizeof(Params), 0, cudaMemcpyHostToDevice, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -1031,9 +1033,9 @@ static cudaError_t launch_dense_t(int grid, size_t smem, cudaStream_t st, const 
 }
 size_t dense_mma_smem(int ntile, int coef_doubles, int nb_max) {
   (void)nb_max;
+  (void)coef_doubles;   // the dense stage needs no coefficients: M comes from X, W from k_patch_flux
   const int NC = 8 * ntile, LDM = NC + 4;
-  return sizeof(double) * ((size_t)coef_doubles + (size_t)NC * LDM + (size_t)kDTB * LDM + 4 * NC) +
-         sizeof(int) * ((size_t)NC * 32 + 8);
+  return sizeof(double) * ((size_t)NC * LDM + 2 * (size_t)kDTB * LDM) + sizeof(int) * ((size_t)NC * 32 + 8);
 }
 cudaError_t launch_patch_dense_mma(int ntile, int grid, size_t smem, cudaStream_t st, const int *ids, int n_work,
                                    const double *coef, const double *X, const double *W, double *Minv, double *G,

@@ -51,7 +51,7 @@ struct FinishLayout {
   long long x_stride;
 };
 
-cudaError_t upload_params(const Params &p);
+cudaError_t upload_params(const Params &p, cudaStream_t st);   // stream-ordered upload of the __constant__ block
 
 cudaError_t launch_patch_solve(int grid, size_t smem, cudaStream_t st, const int *ids, int n_work, const double *coef,
                                double *X, double *Lws, int *status, const SolveLayout &lay);
