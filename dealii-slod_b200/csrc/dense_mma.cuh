@@ -16,6 +16,16 @@ namespace slod {
 
 constexpr int kDTB = 32;    // boundary rows per tile
 
+// one node layer of X (contiguous rows) -> shared memory as four bulk copies on one barrier (several requests in flight)
+__device__ __forceinline__ void stage_layer(double *dst, const double *src, size_t doubles, uint64_t *bar) {
+  mbar_expect_tx(bar, (uint32_t)(doubles * sizeof(double)));
+  const size_t piece = ((doubles + 3) / 4 + 1) & ~(size_t)1;   // even number of doubles: 16-byte granules
+  for (size_t off = 0; off < doubles; off += piece) {
+    const size_t cnt = (doubles - off < piece) ? doubles - off : piece;
+    bulk_g2s(dst + off, src + off, (uint32_t)(cnt * sizeof(double)), bar);
+  }
+}
+
 template <int NTILE>
 __global__ void __launch_bounds__(32 * NTILE, 1)
 k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
@@ -67,13 +77,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     if (staged && tid == 0) {
       // the previous patch used the region through the generic proxy (everybody is past the barrier above)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const uint32_t bytes = (uint32_t)(layer_doubles * sizeof(double));
-      mbar_expect_tx(&sBar[0], bytes);
-      bulk_g2s(sM, X, bytes, &sBar[0]);
-      if (geo.q[2] > 1) {
-        mbar_expect_tx(&sBar[1], bytes);
-        bulk_g2s(sM + layer_doubles, X + layer_doubles, bytes, &sBar[1]);
-      }
+      stage_layer(sM, X, layer_doubles, &sBar[0]);
+      if (geo.q[2] > 1) stage_layer(sM + layer_doubles, X + layer_doubles, layer_doubles, &sBar[1]);
     }
     // ---- table: interior X rows (and weights 1,2,4,8) under every coarse row; one (row, local node) pair per thread,
     // compacted per row by ballot. ----
@@ -119,7 +124,6 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       for (int kz = 0; kz < KZ; ++kz)
 #pragma unroll
         for (int j = 0; j < TW; ++j) acc[kz][j] = 0.0;
-      const uint32_t bytes = (uint32_t)(layer_doubles * sizeof(double));
       for (int zi = 0; zi < geo.q[2]; ++zi) {
         const int b = zi & 1;
         mbar_wait(&sBar[b], (bar_phase >> b) & 1u);
@@ -156,10 +160,8 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
             }
         }
         __syncthreads();   // everybody is done with buffer b
-        if (tid == 0 && zi + 2 < geo.q[2]) {
-          mbar_expect_tx(&sBar[b], bytes);
-          bulk_g2s(sM + (size_t)b * layer_doubles, X + (size_t)(zi + 2) * layer_doubles, bytes, &sBar[b]);
-        }
+        if (tid == 0 && zi + 2 < geo.q[2])
+          stage_layer(sM + (size_t)b * layer_doubles, X + (size_t)(zi + 2) * layer_doubles, layer_doubles, &sBar[b]);
       }
       // all copies have landed and been consumed: M replaces the staging buffers (padding rows/cols: identity)
       const double scale = cP.pw / cP.Hd;
@@ -221,8 +223,12 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       const int nblk = (ncd + 7) >> 3;
       double *sPinvB = sT;           // [2][64] Pinv of step K in buffer K & 1 (row-major); sT is free until the W tiles
       double *sLi = sT + 128;        // [64] scratch: L^{-1}
+      double *sTile = sT + 192;      // [64] the pivot tile itself, row-major
       auto invert_pivot = [&](double2 pv, double *Pinv) {  // one warp: Pinv = (L^{-1})^T L^{-1} of the tile held in C layout
-        badpiv |= chol8_inv(pv.x, pv.y, lane, sLi);
+        *reinterpret_cast<double2 *>(sTile + g * 8 + 2 * t) = pv;
+        __syncwarp();
+        badpiv |= chol8_inv_reg(sTile, 8, lane, sLi);   // shuffle-free: the shortest dependency chain (solve_mma.cuh)
+        __syncwarp();
         double p0 = 0.0, p1 = 0.0;
         const double f0 = sLi[t * 8 + g], f1 = sLi[(4 + t) * 8 + g];  // A[m][k] = Li[k][m] and B[k][n] = Li[k][n]
         dmma884(p0, p1, f0, f0);
