@@ -56,13 +56,14 @@ struct slod_ctx {
   bool chunk_limited = false;
   int64_t ids_cap = 0;   // capacity of d_ids (patches of one range)
   int *d_ids = nullptr;
-  double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr, *d_W = nullptr;
+  double *d_X = nullptr, *d_Minv = nullptr, *d_G = nullptr, *d_cvec = nullptr, *d_Lws = nullptr, *d_W = nullptr, *d_coefws = nullptr;
   FluxLayout xl{};
   size_t smem_flux = 0;
   int grid_flux = 0;
   int solve_grid = 0;
   int dense_ntile = 0;   // 0: generic SIMT dense stage, else tensor-core variant
   int mma_variant = -1;  // -1: generic SIMT solver, else tensor-core solver variant
+  bool dense_coef_gmem = false;   // SIMT dense kernel keeps the patch coefficients in a global scratch (very large patches)
   int mma_threads = 0;
   int mma_nip = 0, mma_stw = 0;
   bool split_solver = false;      // factor + triangular-solve kernels instead of the fused solver (large 3-D patches)
@@ -459,7 +460,8 @@ void free_workspace(slod_ctx *c) {
     if (p) cudaFree(p);
     p = nullptr;
   };
-  F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W);
+  F(c->d_counter); F(c->d_work_counter); F(c->d_ids); F(c->d_X); F(c->d_Minv); F(c->d_G); F(c->d_cvec); F(c->d_Lws); F(c->d_W); F(c->d_coefws);
+  c->dl.coef_ws = nullptr;
   F(c->d_Lrec); F(c->d_stw);
   F(c->sb.eig_list); F(c->sb.jac_list); F(c->sb.H); F(c->sb.V); F(c->sb.rot_cs); F(c->sb.rot_i); F(c->sb.rot_n);
   c->chunk = 0;
@@ -499,6 +501,10 @@ int ensure_workspace(slod_ctx *ctx, int64_t n_range) {
     CK(cudaMalloc(&ctx->d_G, sizeof(double) * (size_t)ctx->dl.m_stride * chunk));
     CK(cudaMalloc(&ctx->d_cvec, sizeof(double) * (size_t)P.s * P.NcdMax * chunk));
     if (ctx->dense_ntile) CK(cudaMalloc(&ctx->d_W, sizeof(double) * (size_t)ctx->xl.w_stride * chunk));
+    if (ctx->dense_coef_gmem) {
+      CK(cudaMalloc(&ctx->d_coefws, sizeof(double) * (size_t)ctx->dl.coef_doubles * ctx->grid_dense));
+      ctx->dl.coef_ws = ctx->d_coefws;
+    }
     if (ctx->split_solver)
     {
       CK(cudaMalloc(&ctx->d_Lrec, sizeof(double) * (size_t)split_rec_stride(ctx->mma_nip) * chunk));
@@ -985,6 +991,10 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   sl.lws_per_cta = (long long)steps_max * (kSolveNB * kSolveNB + bw_max * kSolveNB);
   ctx->smem_solve = sizeof(double) * ((size_t)coef_doubles + (size_t)sl.R * sl.ldw + (size_t)sl.R * sl.ldr +
                                       (size_t)sl.R * kSolveNB + 2 * kSolveNB * kSolveNB + (size_t)kSolveNB * sl.ldr);
+  sl.gmem_window = 0;
+  sl.gwin_off = 0;
+  const size_t smem_solve_small = sizeof(double) * ((size_t)coef_doubles + 2 * kSolveNB * kSolveNB + (size_t)kSolveNB * sl.ldr);
+  const long long gwin_doubles = (long long)sl.R * sl.ldw + (long long)sl.R * sl.ldr + (long long)sl.R * kSolveNB;
   // tensor-core solver when the window (RB blocks of 8 rows) and the coarse columns (NW warps x 8) fit a variant
   {
     const int rb_need = (bw_max + 8 + 7) / 8, nw_need = (P.NcdMax + 7) / 8;
@@ -992,7 +1002,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     if (rb_need <= 13 && nw_need <= 16 && (rb_need > 4 || nw_need > 8)) { variant = 0; rbmax = 13; nw = 16; }
     else if (rb_need <= 4 && nw_need <= 4) { variant = 1; rbmax = 4; nw = 4; }
     else if (rb_need <= 4 && nw_need <= 8) { variant = 2; rbmax = 4; nw = 8; }
-    if (getenv("SLOD_FORCE_SIMT_SOLVER")) variant = -1;
+    if (getenv("SLOD_FORCE_SIMT_SOLVER") || getenv("SLOD_FORCE_GMEM_SOLVER")) variant = -1;
     if (variant >= 0) {
       ctx->mma_variant = variant;
       ctx->mma_threads = 32 * nw;
@@ -1011,6 +1021,13 @@ int slod_create(const slod_params *par, slod_ctx **out) {
         ctx->smem_tri = split_trisolve_smem(nip);
       }
     }
+  }
+  if (ctx->mma_variant < 0 && (ctx->smem_solve > prop.sharedMemPerBlockOptin || getenv("SLOD_FORCE_GMEM_SOLVER"))) {
+    // the SIMT solver with its windows in global memory: the fall-back for patches of any size
+    sl.gmem_window = 1;
+    sl.gwin_off = sl.lws_per_cta;
+    sl.lws_per_cta += gwin_doubles;
+    ctx->smem_solve = smem_solve_small;
   }
   DenseLayout &dl = ctx->dl;
   dl.threads = big ? 512 : 128;
@@ -1035,6 +1052,12 @@ int slod_create(const slod_params *par, slod_ctx **out) {
         dl.threads = 32 * ntile;
       }
     }
+  }
+  dl.coef_ws = nullptr;
+  if (!ctx->dense_ntile && (ctx->smem_dense > prop.sharedMemPerBlockOptin || getenv("SLOD_FORCE_GMEM_SOLVER")) &&
+      ctx->smem_dense - sizeof(double) * (size_t)coef_doubles <= prop.sharedMemPerBlockOptin) {
+    ctx->dense_coef_gmem = true;   // the pointer is set when the workspace is allocated
+    ctx->smem_dense -= sizeof(double) * (size_t)coef_doubles;
   }
   // the split solver keeps its columns in z-major order, which only the tensor-core flux / dense kernels understand
   if (ctx->split_solver && !ctx->dense_ntile) ctx->split_solver = false;

@@ -142,16 +142,19 @@ __global__ void __launch_bounds__(512, 1)
 k_patch_solve(const int *__restrict__ patch_ids, int n_work, const double *__restrict__ d_coef,
               double *__restrict__ Xbuf, double *__restrict__ Lws, int *__restrict__ status, SolveLayout lay) {
   extern __shared__ double smem[];
+  double *myL = Lws + (size_t)blockIdx.x * lay.lws_per_cta;
   double *sCoef = smem;
-  double *sW = sCoef + lay.coef_doubles;
+  // Large patches (e.g. 3-D, 4 subdivisions, oversampling 2: half band width 381): the three windows do not fit shared
+  // memory and live in the CTA's slice of the global workspace (L2 resident); block barriers order the accesses as
+  // they do for shared memory.  Slower, but every configuration the reference's direct solver accepts runs.
+  double *sW = lay.gmem_window ? myL + lay.gwin_off : sCoef + lay.coef_doubles;
   double *sR = sW + (size_t)lay.R * lay.ldw;
   double *sLp = sR + (size_t)lay.R * lay.ldr;
-  double *sLd = sLp + (size_t)lay.R * NB;
+  double *sLd = lay.gmem_window ? sCoef + lay.coef_doubles : sLp + (size_t)lay.R * NB;
   double *sLinv = sLd + NB * NB;
   double *sYd = sLinv + NB * NB;
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int R = lay.R, ldw = lay.ldw, ldr = lay.ldr;
-  double *myL = Lws + (size_t)blockIdx.x * lay.lws_per_cta;
   const int lstep = NB * NB + lay.bw_max * NB;  // doubles per panel in the L workspace
 
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -382,8 +385,8 @@ k_patch_dense(const int *__restrict__ patch_ids, int n_work, const double *__res
               const double *__restrict__ Xbuf, double *__restrict__ Minv_out, double *__restrict__ G_out,
               double *__restrict__ diag, int *__restrict__ status, DenseLayout lay) {
   extern __shared__ double smem[];
-  double *sCoef = smem;
-  double *sM = sCoef + lay.coef_doubles;                 // [ncd][ncd]
+  double *sCoef = lay.coef_ws ? lay.coef_ws + (size_t)blockIdx.x * lay.coef_doubles : smem;
+  double *sM = lay.coef_ws ? smem : sCoef + lay.coef_doubles;   // [ncd][ncd]
   double *sT1 = sM + (size_t)lay.ncd_max * lay.ncd_max;  // [kTB][ncd]  W tile
   double *sT2 = sT1 + kTB * lay.ncd_max;                 // [kTB][ncd]  BD tile
   double *sCol = sT2 + kTB * lay.ncd_max;                // [ncd] pivot column

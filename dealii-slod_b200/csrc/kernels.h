@@ -18,6 +18,8 @@ struct SolveLayout {
   int ldx;           // leading dimension of X rows (NcdMax)
   long long x_stride;     // doubles per patch in Xbuf (NiMax * ldx)
   long long lws_per_cta;  // doubles of L workspace per CTA
+  int gmem_window;        // patches too large for shared memory: the band / RHS / panel windows live in the CTA's
+  long long gwin_off;     //   slice of the L workspace instead, at this offset (doubles)
 };
 struct DenseLayout {
   long long w_stride;  // doubles per patch in the flux buffer W
@@ -28,6 +30,7 @@ struct DenseLayout {
   long long x_stride;
   long long m_stride;  // ncd_max^2
   int zmajor;          // coarse columns in the z-major order of the split solver (geom.h)
+  double *coef_ws;     // SIMT kernel, very large patches: per-CTA coefficient window in global memory (else nullptr)
 };
 struct FluxLayout {
   int coef_doubles;

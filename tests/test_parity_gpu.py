@@ -72,13 +72,50 @@ CASES = [
     dict(dim=3, s=1, ref=1, n=2, ell=1),
     dict(dim=3, s=1, ref=2, n=2, ell=1),
     dict(dim=3, s=1, ref=3, n=2, ell=2, sample=10, kind="uniform1e4", seed=3001),   # cfg 4 shape
+    # patches too large for the shared-memory solvers (Ni = 3375, half band width 241): windows in global memory
+    dict(dim=3, s=1, ref=2, n=4, ell=2, sample=6),
+    # the same fall-back forced on small shapes (SIMT solver with global windows, SIMT dense with a global coefficient window)
+    dict(dim=2, s=1, ref=3, n=2, ell=1, env="SLOD_FORCE_GMEM_SOLVER"),
+    dict(dim=2, s=2, ref=3, n=2, ell=1, env="SLOD_FORCE_GMEM_SOLVER"),
+    dict(dim=3, s=1, ref=2, n=2, ell=1, env="SLOD_FORCE_GMEM_SOLVER"),
 ]
 
 
+def test_large_patches_global_memory_solver():
+    """3-D patches with 4 subdivisions and oversampling 2 (Ni = 6859 interior dofs, half band width 381,
+    125 coarse dofs) do not fit the shared-memory solvers; the SIMT solver runs them with its band / right-hand-side
+    windows in global memory -- a direct banded Cholesky like the reference's direct solver (include/LODtools.h:575-580)."""
+    ctx, orc = build_pair(dim=3, s=1, ref=3, n=4, ell=2)
+    ctx.compute_basis()
+    ctx.assemble_coarse()
+    full = next(p for p in range(ctx.n_patches) if ctx.patch_info(p)["n_cells"] == 125)
+    assert ctx.patch_info(full)["n_internal"] == 6859
+    pids = [0, full, ctx.n_patches - 1]
+    orc.compute_basis(pids)
+    for res in orc.patches:
+        phi, aphi = ctx.basis(res.pid)
+        dg = ctx.diagnostics(res.pid)
+        assert dg[7] == 0
+        if not margin_safe(res.info, 0):
+            continue
+        assert int(dg[1]) == res.info["trunc_steps"][0]
+        tol = max(1e-10, 50.0 * selection_sensitivity(res.info, 0))
+        assert np.linalg.norm(phi - res.basis[0]) <= tol, (res.pid, tol)
+        assert np.linalg.norm(aphi - res.basis_premultiplied[0]) <= 10 * tol * np.linalg.norm(res.basis_premultiplied[0])
+    rowptr, col, val = ctx.coarse_csr()
+    K = np.zeros((ctx.n_patches, ctx.n_patches))
+    for i in range(ctx.n_patches):
+        K[i, col[rowptr[i]:rowptr[i + 1]]] = val[rowptr[i]:rowptr[i + 1]]
+    assert np.abs(K - K.T).max() <= 1e-8 * np.abs(K).max()
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_basis_and_coarse_matrix(case):
+def test_basis_and_coarse_matrix(case, monkeypatch):
     case = dict(case)
     sample = case.pop("sample", None)
+    env = case.pop("env", None)
+    if env:
+        monkeypatch.setenv(env, "1")   # read by slod_create
     ctx, orc = build_pair(**case)
     s = case["s"]
     ctx.compute_basis()
