@@ -788,8 +788,9 @@ k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const d
 // each member's own box), so every A*phi value of a neighbour is loaded once per group and multiplied with all
 // members' phi at the same shared-memory offset: no per-pair index arithmetic, 2^dim times less L2 traffic.
 // ------------------------------------------------------------------------------------------------
+constexpr int kCoarseThreads = 1024;   // 32 warps: the kernel is bound by the latency of its L2 / shared-memory loads
 template <int DIM, int S>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kCoarseThreads, 1)
 k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi, const double *__restrict__ aphi,
                  double *__restrict__ Kell, FinishLayout lay, int NU) {
   constexpr int NG = 1 << DIM;   // patches per group
@@ -918,7 +919,7 @@ static cudaError_t launch_coarse_blocked_t(int grid, size_t smem, cudaStream_t s
   // slots of neighbours outside the domain are never visited: clear the rows first
   e = cudaMemsetAsync(Kell + (size_t)p0 * S * (lay.ell_width), 0, sizeof(double) * (size_t)(p1 - p0) * S * lay.ell_width, st);
   if (e != cudaSuccess) return e;
-  k_coarse_blocked<DIM, S><<<grid, 512, smem, st>>>(p0, p1, phi, aphi, Kell, lay, NU);
+  k_coarse_blocked<DIM, S><<<grid, kCoarseThreads, smem, st>>>(p0, p1, phi, aphi, Kell, lay, NU);
   return cudaGetLastError();
 }
 size_t coarse_blocked_smem(int dim, int s, int NU) {
