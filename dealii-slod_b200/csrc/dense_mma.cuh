@@ -265,28 +265,33 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         __syncthreads();
         PH(9)
         if (warp != K && warp < nblk) {
-          // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments, sweeps J three tiles at a time ----
+          // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments and sweeps its row four tiles at a time.  Fully
+          // unrolled over the tile index with running base pointers, so that a tile costs its three loads, two tensor
+          // instructions and one store and nothing else: with index arithmetic per tile the sweep was bound by the
+          // instruction issue rate, not by the tensor pipe.  Tile K itself is swept too (result dropped). ----
           const int I = warp;
-          const double a0 = -sM[(8 * I + g) * LDM + 8 * K + t], a1 = -sM[(8 * I + g) * LDM + 8 * K + 4 + t];
-          for (int J0 = 0; J0 < nblk; J0 += 3) {
-            double2 c[3];
-            double b0[3], b1[3];
+          const double *arow = sM + (8 * I + g) * LDM;
+          double *crow = sM + (8 * I + g) * LDM + 2 * t;
+          const double *br0 = sM + (8 * K + t) * LDM + g, *br1 = br0 + 4 * LDM;
+          const double a0 = -arow[8 * K + t], a1 = -arow[8 * K + 4 + t];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-              int J = J0 + u;
-              if (J >= nblk || J == K) J = (K == 0) ? 1 : 0;   // dummy tile (not stored)
-              c[u] = *reinterpret_cast<const double2 *>(sM + (8 * I + g) * LDM + 8 * J + 2 * t);
-              b0[u] = sM[(8 * K + t) * LDM + 8 * J + g];
-              b1[u] = sM[(8 * K + 4 + t) * LDM + 8 * J + g];
-            }
+          for (int J0 = 0; J0 < NTILE; J0 += 4) {
+            if (J0 < nblk) {
+              double2 c[4];
+              double b0[4], b1[4];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
+              for (int u = 0; u < 4; ++u) {
+                c[u] = *reinterpret_cast<const double2 *>(crow + 8 * (J0 + u));
+                b0[u] = br0[8 * (J0 + u)];
+                b1[u] = br1[8 * (J0 + u)];
+              }
 #pragma unroll
-            for (int u = 0; u < 3; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+              for (int u = 0; u < 4; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
 #pragma unroll
-            for (int u = 0; u < 3; ++u) {
-              const int J = J0 + u;
-              if (J < nblk && J != K) *reinterpret_cast<double2 *>(sM + (8 * I + g) * LDM + 8 * J + 2 * t) = c[u];
+              for (int u = 0; u < 4; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (J0 + u != K && J0 + u < nblk) *reinterpret_cast<double2 *>(crow + 8 * (J0 + u)) = c[u];
             }
           }
           // ---- column block: M_IK = -M_IK Pinv.  Only warp I reads or writes tile (I, K) in this step, and the mma is
@@ -301,10 +306,13 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
             dmma884(la_c.x, la_c.y, la_a1, sM[(8 * K + 4 + t) * LDM + 8 * (K + 1) + g]);
             invert_pivot(la_c, sPinvB + ((K + 1) & 1) * 64);
           }
-          // M_KK = Pinv (nobody reads tile (K, K) in this step)
+          // M_KK = Pinv (tile (K, K) is only read by the dropped dummy sweep of column K in this step)
           *reinterpret_cast<double2 *>(sM + (8 * K + g) * LDM + 8 * K + 2 * t) =
               *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
         }
+#ifdef SLOD_PHASE_CLOCKS
+        if (ph_on) { const long long c_ = clock64(); ph_acc[(warp == K) ? 4 : 11] += c_ - ph_last; ph_last = c_; }
+#endif
         __syncthreads();
         PH(10)
       }
