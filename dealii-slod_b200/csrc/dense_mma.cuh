@@ -223,10 +223,9 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
       const int nblk = (ncd + 7) >> 3;
       double *sPinvB = sT;           // [2][64] Pinv of step K in buffer K & 1 (row-major); sT is free until the W tiles
       double *sLi = sT + 128;        // [64] scratch: L^{-1}
-      double *sTile = sT + 192;      // [64] the pivot tile itself, row-major
-      auto invert_pivot = [&](double2 pv, double *Pinv) {  // one warp: Pinv = (L^{-1})^T L^{-1} of the tile held in C layout
-        *reinterpret_cast<double2 *>(sTile + g * 8 + 2 * t) = pv;
-        __syncwarp();
+      double *sTile = sT + 192;      // [64] the next pivot tile, row-major (published by its owner, inverted by warp K)
+      double *sRowB = sT + 256;      // [2][8][LDM] block row K (buffer K & 1): first as it is, then multiplied with Pinv
+      auto invert_pivot = [&](double *Pinv) {  // one warp: Pinv = (L^{-1})^T L^{-1} of the tile in sTile
         badpiv |= chol8_inv_reg(sTile, 8, lane, sLi);   // shuffle-free: the shortest dependency chain (solve_mma.cuh)
         __syncwarp();
         double p0 = 0.0, p1 = 0.0;
@@ -235,80 +234,113 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         dmma884(p0, p1, f1, f1);
         *reinterpret_cast<double2 *>(Pinv + g * 8 + 2 * t) = make_double2(p0, p1);
       };
-      if (warp == 0) invert_pivot(*reinterpret_cast<const double2 *>(sM + g * LDM + 2 * t), sPinvB);
+      // Warp I keeps block row I in registers for the whole elimination (NTILE tiles in C-fragment layout, 2 doubles
+      // each).  With the rows in shared memory every tile of the rank-8 sweep cost a 16-byte load and store (2-way
+      // bank conflicts: the row stride suits the 8-byte fragment loads of the BD phase) on top of its B operand, and
+      // the sweep was bound by shared-memory wavefronts, not by the tensor pipe.  Only the pivot row passes through
+      // shared memory: its owner writes it at the end of the previous step, every warp multiplies one tile with Pinv
+      // in place, the sweeps read their B operands from it, and the owner takes it back at the end of the step.
+      double2 c[NTILE];
+      const bool rowwarp = warp < nblk;
+      const int frag = g * LDM + 2 * t;   // C-fragment position of this lane inside a block row
+#pragma unroll
+      for (int J = 0; J < NTILE; ++J)
+        c[J] = (rowwarp && J < nblk) ? *reinterpret_cast<const double2 *>(sM + 8 * warp * LDM + frag + 8 * J)
+                                     : make_double2(0.0, 0.0);
+      if (warp == 0) {
+        *reinterpret_cast<double2 *>(sTile + g * 8 + 2 * t) = c[0];
+#pragma unroll
+        for (int J = 0; J < NTILE; ++J)
+          if (J < nblk) *reinterpret_cast<double2 *>(sRowB + frag + 8 * J) = c[J];
+        __syncwarp();
+        invert_pivot(sPinvB);
+      }
       __syncthreads();
-      // Two barriers per step.  Warp K owns the pivot row and has no tile to update in step K: it looks ahead instead --
-      // it forms the final value of the next pivot block (K+1, K+1) in registers (the same two DMMAs warp K+1 applies to
-      // that tile, so the bits agree) and inverts it into the other Pinv buffer while the others sweep their rows.
       for (int K = 0; K < nblk; ++K) {
         PH(2)
         const double *sPinv = sPinvB + (K & 1) * 64;
-        double2 la_c = make_double2(0.0, 0.0);
-        double la_a0 = 0.0, la_a1 = 0.0;
-        const bool lookahead = (warp == K) && (K + 1 < nblk);
-        // ---- R_KJ = Pinv M_KJ, in place; NTILE - 1 tiles over the warps (warp J handles tile J) ----
-        if (warp != K && warp < nblk) {
+        double *sRow = sRowB + (K & 1) * 8 * LDM;
+        const bool have_next = K + 1 < nblk;
+        // ---- R_KJ = Pinv M_KJ, in place in the row buffer; warp J handles tile J ----
+        if (rowwarp && warp != K) {
           const int J = warp;
-          double *ct = sM + (8 * K + g) * LDM + 8 * J + 2 * t;
-          const double b0 = sM[(8 * K + t) * LDM + 8 * J + g], b1 = sM[(8 * K + 4 + t) * LDM + 8 * J + g];
+          const double b0 = sRow[t * LDM + 8 * J + g], b1 = sRow[(4 + t) * LDM + 8 * J + g];
           double r0_ = 0.0, r1_ = 0.0;
           dmma884(r0_, r1_, sPinv[g * 8 + t], b0);
           dmma884(r0_, r1_, sPinv[g * 8 + 4 + t], b1);
           __syncwarp();
-          *reinterpret_cast<double2 *>(ct) = make_double2(r0_, r1_);
-        } else if (lookahead) {   // block row K + 1 is not touched in this phase
-          const double *rowp = sM + (8 * (K + 1) + g) * LDM;
-          la_c = *reinterpret_cast<const double2 *>(rowp + 8 * (K + 1) + 2 * t);
-          la_a0 = -rowp[8 * K + t];
-          la_a1 = -rowp[8 * K + 4 + t];
+          *reinterpret_cast<double2 *>(sRow + frag + 8 * J) = make_double2(r0_, r1_);
         }
         __syncthreads();
         PH(9)
-        if (warp != K && warp < nblk) {
-          // ---- M_IJ -= M_IK R_KJ : warp I keeps its A fragments and sweeps its row four tiles at a time.  Fully
-          // unrolled over the tile index with running base pointers, so that a tile costs its three loads, two tensor
-          // instructions and one store and nothing else: with index arithmetic per tile the sweep was bound by the
-          // instruction issue rate, not by the tensor pipe.  Tile K itself is swept too (result dropped). ----
-          const int I = warp;
-          const double *arow = sM + (8 * I + g) * LDM;
-          double *crow = sM + (8 * I + g) * LDM + 2 * t;
-          const double *br0 = sM + (8 * K + t) * LDM + g, *br1 = br0 + 4 * LDM;
-          const double a0 = -arow[8 * K + t], a1 = -arow[8 * K + 4 + t];
+        if (rowwarp && warp != K) {
+          // A fragments {(g, t), (g, 4 + t)} of the own column-K tile out of its C-fragment registers: element (g, col)
+          // sits in lane 4 g + (col >> 1), slot col & 1
+          double2 ck = c[0];
+#pragma unroll
+          for (int J = 1; J < NTILE; ++J) ck = (J == K) ? c[J] : ck;
+          const double x0 = __shfl_sync(0xffffffffu, ck.x, 4 * g + (t >> 1)), y0 = __shfl_sync(0xffffffffu, ck.y, 4 * g + (t >> 1));
+          const double x1 = __shfl_sync(0xffffffffu, ck.x, 4 * g + 2 + (t >> 1)), y1 = __shfl_sync(0xffffffffu, ck.y, 4 * g + 2 + (t >> 1));
+          const double a0 = -((t & 1) ? y0 : x0), a1 = -((t & 1) ? y1 : x1);
+          const double *br0 = sRow + t * LDM + g, *br1 = br0 + 4 * LDM;
+          const bool is_next = have_next && warp == K + 1;
+          if (is_next) {
+            // the next pivot block first: publish it for warp K's look-ahead inversion
+            double2 cn = c[0];
+#pragma unroll
+            for (int J = 1; J < NTILE; ++J) cn = (J == K + 1) ? c[J] : cn;
+            dmma884(cn.x, cn.y, a0, br0[8 * (K + 1)]);
+            dmma884(cn.x, cn.y, a1, br1[8 * (K + 1)]);
+#pragma unroll
+            for (int J = 0; J < NTILE; ++J) c[J] = (J == K + 1) ? cn : c[J];
+            *reinterpret_cast<double2 *>(sTile + g * 8 + 2 * t) = cn;
+            __syncwarp();
+            asm volatile("bar.arrive 1, 64;" ::: "memory");
+          }
+          const int jskip = is_next ? K + 1 : -1;
+          // ---- M_IJ -= M_IK R_KJ over the row, four tiles in flight ----
 #pragma unroll
           for (int J0 = 0; J0 < NTILE; J0 += 4) {
             if (J0 < nblk) {
-              double2 c[4];
               double b0[4], b1[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                c[u] = *reinterpret_cast<const double2 *>(crow + 8 * (J0 + u));
                 b0[u] = br0[8 * (J0 + u)];
                 b1[u] = br1[8 * (J0 + u)];
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) dmma884(c[u].x, c[u].y, a0, b0[u]);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) dmma884(c[u].x, c[u].y, a1, b1[u]);
+              for (int u = 0; u < 4; ++u)
+                if (J0 + u != K && J0 + u != jskip && J0 + u < nblk) dmma884(c[J0 + u].x, c[J0 + u].y, a0, b0[u]);
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (J0 + u != K && J0 + u < nblk) *reinterpret_cast<double2 *>(crow + 8 * (J0 + u)) = c[u];
+                if (J0 + u != K && J0 + u != jskip && J0 + u < nblk) dmma884(c[J0 + u].x, c[J0 + u].y, a1, b1[u]);
             }
           }
-          // ---- column block: M_IK = -M_IK Pinv.  Only warp I reads or writes tile (I, K) in this step, and the mma is
-          // warp synchronous (every lane has loaded its fragment before any lane stores) ----
+          // ---- column block: M_IK = -M_IK Pinv ----
           double2 newcol = make_double2(0.0, 0.0);
           dmma884(newcol.x, newcol.y, a0, sPinv[t * 8 + g]);
           dmma884(newcol.x, newcol.y, a1, sPinv[(4 + t) * 8 + g]);
-          *reinterpret_cast<double2 *>(sM + (8 * I + g) * LDM + 8 * K + 2 * t) = newcol;
-        } else if (warp == K) {
-          if (lookahead) {
-            dmma884(la_c.x, la_c.y, la_a0, sM[(8 * K + t) * LDM + 8 * (K + 1) + g]);
-            dmma884(la_c.x, la_c.y, la_a1, sM[(8 * K + 4 + t) * LDM + 8 * (K + 1) + g]);
-            invert_pivot(la_c, sPinvB + ((K + 1) & 1) * 64);
+#pragma unroll
+          for (int J = 0; J < NTILE; ++J) c[J] = (J == K) ? newcol : c[J];
+          if (is_next) {   // the pivot row of the next step goes to the other row buffer
+            double *nrow = sRowB + ((K + 1) & 1) * 8 * LDM + frag;
+#pragma unroll
+            for (int J = 0; J < NTILE; ++J)
+              if (J < nblk) *reinterpret_cast<double2 *>(nrow + 8 * J) = c[J];
           }
-          // M_KK = Pinv (tile (K, K) is only read by the dropped dummy sweep of column K in this step)
-          *reinterpret_cast<double2 *>(sM + (8 * K + g) * LDM + 8 * K + 2 * t) =
-              *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
+        } else if (warp == K) {
+          // the look-ahead: invert the next pivot block into the other Pinv buffer (the row registers are dead here) ...
+          if (have_next) {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            invert_pivot(sPinvB + ((K + 1) & 1) * 64);
+          }
+          // ... then take the row back: M_KJ = R_KJ, M_KK = Pinv
+#pragma unroll
+          for (int J = 0; J < NTILE; ++J)   // every register is overwritten: nothing of the row stays live across the inversion
+            c[J] = (J < nblk) ? *reinterpret_cast<const double2 *>(sRow + frag + 8 * J) : make_double2(0.0, 0.0);
+          const double2 pk = *reinterpret_cast<const double2 *>(sPinv + g * 8 + 2 * t);
+#pragma unroll
+          for (int J = 0; J < NTILE; ++J) c[J] = (J == K) ? pk : c[J];
         }
 #ifdef SLOD_PHASE_CLOCKS
         if (ph_on) { const long long c_ = clock64(); ph_acc[(warp == K) ? 4 : 11] += c_ - ph_last; ph_last = c_; }
@@ -316,6 +348,12 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         __syncthreads();
         PH(10)
       }
+      if (rowwarp) {
+#pragma unroll
+        for (int J = 0; J < NTILE; ++J)
+          if (J < nblk) *reinterpret_cast<double2 *>(sM + 8 * warp * LDM + frag + 8 * J) = c[J];
+      }
+      __syncthreads();
       if (badpiv && lane == 0) atomicOr(&status[pid], 2);
       double *Mo = Minv_out + (size_t)w * lay.m_stride;
       for (int idx = tid; idx < ncd * NC; idx += NT) {
@@ -349,6 +387,15 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
     const int ksteps = (ncd + 3) >> 2;
     const int I1 = warp % (NTILE / 2), I2 = NTILE - 1 - I1;
     const int e_base = (warp / (NTILE / 2)) * NGA;   // first entry of this warp in the pair's list of NTILE + 1 tiles
+    int gcol[NGA];          // B column (doubles) of the el-th owned tile
+    unsigned gfirst = 0;    // bit el: the tile belongs to tile row I1 (else I2)
+#pragma unroll
+    for (int el = 0; el < NGA; ++el) {
+      const int e = e_base + el;
+      const bool first = (e <= I1);
+      gcol[el] = (e > NTILE) ? 0 : 8 * (first ? e : e - (I1 + 1));
+      gfirst |= (first ? 1u : 0u) << el;
+    }
     // W = S_b X - P_b comes from k_patch_flux, zero padded to whole tiles.  The tiles alternate between two buffers:
     // a thread moves 64 bytes of a tile with cp.async (NT * 8 = 32 * NC doubles), tile i + 1 is in flight while the
     // tensor phases of tile i run, and BD replaces W in the tile's own buffer.
@@ -385,18 +432,23 @@ k_patch_dense_mma(const int *__restrict__ patch_ids, int n_work, const double *_
         *reinterpret_cast<double2 *>(sW + (8 * i + g) * LDM + 8 * warp + 2 * t) = make_double2(bd[i][0], bd[i][1]);
       __syncthreads();
       PH(6)
-      // G += BD^T BD on the owned lower-triangle tiles
+      // G += BD^T BD on the owned lower-triangle tiles.  One pointer per tile (its B column, fixed for the patch), the
+      // rows advance by compile-time offsets: a tile step is one load, the select of its A operand and the tensor
+      // instruction -- with four warps per scheduler the phase is bound by the issue rate as soon as a tile step
+      // costs more than four instructions.  A warp's unused ninth slot recomputes tile 0 into an accumulator that is
+      // never stored.
+      {
+        const double *rp = sW + t * LDM + g;
+        const double *pa1 = rp + 8 * I1, *pa2 = rp + 8 * I2;
+        const double *pb[NGA];
 #pragma unroll
-      for (int jj = 0; jj < kDTB / 4; ++jj) {
-        const double *rowp = sW + (4 * jj + t) * LDM + g;
-        const double a1 = rowp[8 * I1], a2 = rowp[8 * I2];
+        for (int el = 0; el < NGA; ++el) pb[el] = rp + gcol[el];
 #pragma unroll
-        for (int el = 0; el < NGA; ++el) {
-          const int e = e_base + el;
-          if (e > NTILE) continue;
-          const bool first = (e <= I1);
-          const int J = first ? e : e - (I1 + 1);
-          dmma884(gacc[el][0], gacc[el][1], first ? a1 : a2, rowp[8 * J]);
+        for (int jj = 0; jj < kDTB / 4; ++jj) {
+          const double a1 = pa1[4 * jj * LDM], a2 = pa2[4 * jj * LDM];
+#pragma unroll
+          for (int el = 0; el < NGA; ++el)
+            dmma884(gacc[el][0], gacc[el][1], ((gfirst >> el) & 1) ? a1 : a2, pb[el][4 * jj * LDM]);
         }
       }
       PH(7)
