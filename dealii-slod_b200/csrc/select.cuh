@@ -324,17 +324,26 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
         }
       }
       if (tau != 0.0) {   // identical in every warp (same data, same arithmetic)
-        // ---- p = tau A22 v : one row per warp pass, lanes over the columns ----
-        for (int i = warp; i < m; i += NWARP) {
-          const double *row = sA + (k + 1 + i) * ld + (k + 1);
-          double acc = 0.0;
+        // ---- p = tau A22 v : eight rows per warp pass (rows warp + NWARP u), lanes over the columns, one packed
+        // reduction for the eight sums (9 shuffles instead of 40 on the latency path of every step) ----
+        for (int i0 = 0; i0 < m; i0 += 8 * NWARP) {
+          double acc[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = lane + 32 * q;
-            if (j < m) acc += row[j] * vq[q];
+          for (int u = 0; u < 8; ++u) {
+            acc[u] = 0.0;
+            const int i = i0 + warp + NWARP * u;
+            if (i < m) {
+              const double *row = sA + (k + 1 + i) * ld + (k + 1);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int j = lane + 32 * q;
+                if (j < m) acc[u] += row[j] * vq[q];
+              }
+            }
           }
-          acc = warp_sum(acc);
-          if (lane == 0) sPv[i] = tau * acc;
+          const double tot = warp_sum_packed(acc, lane);   // lane L holds row index warp_sum_index<8>(L)
+          const int i = i0 + warp + NWARP * warp_sum_index<8>(lane);
+          if ((lane & 3) == 0 && i < m) sPv[i] = tau * tot;
         }
         __syncthreads();
         // ---- w = p - (tau/2)(p.v) v  (every warp), A22 <- A22 - v w^T - w v^T ----
