@@ -1096,12 +1096,16 @@ cudaError_t launch_select_pipeline(const SelectPlan &pl, cudaStream_t st, const 
       ids, n_work, Minv, G, cvec, diag, b.counters, pl.use_ql ? b.eig_list : b.jac_list, pl.use_ql ? 1 : 2, pl.lay);
   ++*n_launches;
   if (pl.use_ql) {
-    SLOD_ATTR(k_eig_tridiag, pl.smem_tri);
+    SLOD_ATTR(k_eig_tridiag<4>, pl.smem_tri);
+    SLOD_ATTR(k_eig_tridiag<8>, pl.smem_tri);
     SLOD_ATTR(k_eig_ql, pl.smem_ql);
     SLOD_ATTR(k_eig_finish, pl.smem_fin);
     const long long items_max = (long long)n_work * pl.s;
     for (long long off = 0; off < items_max; off += pl.eig.cap_items) {
-      k_eig_tridiag<<<pl.grid_tri, 512, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
+      if (pl.eig.nmax - 1 <= 128)   // n = ncd - 1 columns: four per lane are enough
+        k_eig_tridiag<4><<<pl.grid_tri, 512, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
+      else
+        k_eig_tridiag<8><<<pl.grid_tri, 512, pl.smem_tri, st>>>(ids, b.counters, b.eig_list, (int)off, G, b.H, b.V, pl.eig);
       k_eig_ql<<<pl.grid_ql, 256, pl.smem_ql, st>>>(ids, b.counters, b.eig_list, (int)off, b.V, b.rot_cs, b.rot_i,
                                                    b.rot_n, pl.eig);
       k_eig_finish<<<pl.grid_fin, 128, pl.smem_fin, st>>>(ids, b.counters, b.eig_list, (int)off, Minv, b.H, b.V,

@@ -54,6 +54,14 @@ __device__ __forceinline__ void minv_times_selection(const double *__restrict__ 
 // 8 x 8 tiles of the packed lower triangle: tile (I, J), I >= J, at tri(I) + J; inside a tile element (r, c) sits at
 // r * 8 + (c ^ 4 * ((r >> 1) & 1)): A-fragment, transposed-B-fragment and C-fragment accesses are bank-conflict free.
 __device__ __forceinline__ int tile_off(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }
+// row I of entry `idx` of the packed lower triangle (idx = I (I + 1) / 2 + J, J <= I): closed form with one
+// correction step instead of a linear search (the search took a quarter of k_select_fast's issue slots)
+__device__ __forceinline__ int tri_row(int idx) {
+  int I = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+  if ((I + 1) * (I + 2) / 2 <= idx) ++I;
+  if (I * (I + 1) / 2 > idx) --I;
+  return I;
+}
 __device__ __forceinline__ int tile_el(int r, int c) { return r * 8 + (c ^ (((r >> 1) & 1) << 2)); }
 
 __global__ void __launch_bounds__(256, 3)
@@ -103,8 +111,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
         dmax = warp_max(dmax);  // every warp computes it (same value)
         for (int idx = tid; idx < nbk * (nbk + 1) / 2 * 64; idx += NT) {
           const int tile = idx >> 6, e = idx & 63, r = e >> 3, c = e & 7;
-          int I = 0;
-          while ((I + 1) * (I + 2) / 2 <= tile) ++I;
+          const int I = tri_row(tile);
           const int J = tile - I * (I + 1) / 2;
           const int i = 8 * I + r, j = 8 * J + c;
           double v;
@@ -148,8 +155,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
             for (int u = 0; u < 2; ++u) {
               int tu = tt + u * NWARP;
               if (tu >= ntile) tu = tt;
-              int oi = 0;
-              while ((oi + 1) * (oi + 2) / 2 <= tu) ++oi;
+              const int oi = tri_row(tu);
               const int oj = tu - oi * (oi + 1) / 2;
               const int I = K + 1 + oi, J = K + 1 + oj;
               ct[u] = sL + tile_off(I, J);
@@ -245,6 +251,7 @@ k_select_fast(const int *__restrict__ patch_ids, int n_work, const double *__res
 // Per item in HBM:  Hbuf [n][ldh]  row k = Householder vector v_k (v_k[0] = 1, length n-k-1)
 //                   Vbuf [6][nmax] d | e | tau | g_h | (lambda) | (ghat)
 
+template <int QN>   // 32 QN >= n: matrix columns per lane
 __global__ void __launch_bounds__(512, 1)
 k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counters, const int *__restrict__ eig_list,
               int round_off, const double *__restrict__ G_in, double *__restrict__ Hbuf, double *__restrict__ Vbuf,
@@ -279,10 +286,10 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
     for (int k = 0; k < n - 1; ++k) {
       const int m = n - k - 1;  // x = A[k+1 .. n-1][k]
       // ---- reflector H = I - tau v v^T with H x = beta e_1 (every warp) ----
-      double vq[8];
+      double vq[QN];
       double sig = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < QN; ++q) {
         const int i = lane + 32 * q;
         vq[q] = (i < m) ? sA[(k + 1 + i) * ld + k] : 0.0;
         if (i >= 1) sig += vq[q] * vq[q];
@@ -296,7 +303,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
         scal = 1.0 / (alpha - beta);
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < QN; ++q) {
         const int i = lane + 32 * q;
         vq[q] = (i < m) ? ((i == 0) ? 1.0 : vq[q] * scal) : 0.0;
         if (i < m) sv[i] = vq[q];
@@ -304,7 +311,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
       if (warp == 0) {
         double gd = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < QN; ++q) {
           const int i = lane + 32 * q;
           if (i < m) {
             H[(size_t)k * lay.ldh + i] = vq[q];
@@ -313,7 +320,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
         }
         gd = warp_sum(gd) * tau;  // g <- H g
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < QN; ++q) {
           const int i = lane + 32 * q;
           if (i < m) sgv[k + 1 + i] -= gd * vq[q];
         }
@@ -335,7 +342,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
             if (i < m) {
               const double *row = sA + (k + 1 + i) * ld + (k + 1);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < QN; ++q) {
                 const int j = lane + 32 * q;
                 if (j < m) acc[u] += row[j] * vq[q];
               }
@@ -347,10 +354,10 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
         }
         __syncthreads();
         // ---- w = p - (tau/2)(p.v) v  (every warp), A22 <- A22 - v w^T - w v^T ----
-        double wq[8];
+        double wq[QN];
         double dot = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < QN; ++q) {
           const int i = lane + 32 * q;
           wq[q] = (i < m) ? sPv[i] : 0.0;
           dot += wq[q] * vq[q];
@@ -358,7 +365,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
         dot = warp_sum(dot);
         const double al = -0.5 * tau * dot;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < QN; ++q) {
           const int i = lane + 32 * q;
           wq[q] += al * vq[q];
           if (i < m) sw[i] = wq[q];
@@ -368,7 +375,7 @@ k_eig_tridiag(const int *__restrict__ patch_ids, const int *__restrict__ counter
           const double vi = sv[i], wi = sw[i];
           double *row = sA + (k + 1 + i) * ld + (k + 1);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < QN; ++q) {
             const int j = lane + 32 * q;
             if (j < m) row[j] -= vi * wq[q] + wi * vq[q];
           }
