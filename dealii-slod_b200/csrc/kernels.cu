@@ -668,6 +668,31 @@ k_patch_finish(const int *__restrict__ patch_ids, int n_work, const double *__re
           const int ca = i % s;
           if (node_class(cP, g, a) & 2) {
             av = v;  // domain-boundary rows of semi_constrained are identity rows (source/LOD.cc:537-541)
+          } else if (cP.dim == 3 && s == 1 && cP.problem == 0 && !cP.gauss_coef) {
+            // scalar 3-D problem with one coefficient per sub-cell: the same sums in the same order as the general
+            // branch below, fully unrolled -- the 27 phi values around the node are loaded once, the reference-matrix
+            // entries are immediate constant-bank operands, sub-cells outside the patch enter with coefficient 0
+            const int msx = g.m[0] * cP.n, msy = g.m[1] * cP.n, msz = g.m[2] * cP.n;
+            double pn[27];
+#pragma unroll
+            for (int e = 0; e < 27; ++e) {
+              const int bx = a[0] + e % 3 - 1, by = a[1] + (e / 3) % 3 - 1, bz = a[2] + e / 9 - 1;
+              const bool in = bx >= 0 && bx < g.p[0] && by >= 0 && by < g.p[1] && bz >= 0 && bz < g.p[2];
+              pn[e] = in ? sPhi[(bz * g.p[1] + by) * g.p[0] + bx] : 0.0;
+            }
+#pragma unroll
+            for (int oc = 0; oc < 8; ++oc) {
+              const int ox = a[0] - (oc & 1), oy = a[1] - ((oc >> 1) & 1), oz = a[2] - ((oc >> 2) & 1);
+              const bool in = ox >= 0 && ox < msx && oy >= 0 && oy < msy && oz >= 0 && oz < msz;
+              double racc = 0.0;
+#pragma unroll
+              for (int lb = 0; lb < 8; ++lb) {
+                // vertex lb of the sub-cell with origin node - bits(oc): offset bits(lb) - bits(oc) from the node
+                const int ex = (lb & 1) - (oc & 1) + 1, ey = ((lb >> 1) & 1) - ((oc >> 1) & 1) + 1, ez = ((lb >> 2) & 1) - ((oc >> 2) & 1) + 1;
+                racc += cP.Kref[oc * 8 + lb] * pn[(ez * 3 + ey) * 3 + ex];
+              }
+              if (in) av += sCoef[(oz * msy + oy) * msx + ox] * racc;
+            }
           } else {
             // sub-cell-wise application of the patch operator: for every sub-cell that contains the node, its local
             // matrix row times the local phi values (include/Diffusion.h:143-193 / include/Elasticity.h:211-284)
