@@ -1122,7 +1122,7 @@ int slod_create(const slod_params *par, slod_ctx **out) {
   sp.grid_fin = ctx->n_sm * per_sm(sp.smem_fin, 128);
   sp.grid_ql = ctx->n_sm * 8;
   ctx->grid_finish = ctx->n_sm * per_sm(ctx->smem_finish, 256);
-  ctx->grid_flux = ctx->n_sm * std::min(4, per_sm(ctx->smem_flux, 256));
+  ctx->grid_flux = ctx->n_sm * std::min(getenv("SLOD_FLUX_CTAS") ? atoi(getenv("SLOD_FLUX_CTAS")) : 4, per_sm(ctx->smem_flux, 256));   // env: experiments
   ctx->grid_coarse = ctx->n_sm * per_sm(ctx->smem_coarse, 256);
 
   auto cuda_bad = [&](const char *what, cudaError_t e) {
