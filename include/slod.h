@@ -26,9 +26,14 @@
  *    handles into one NCCL communicator and slod_offline_distributed runs the phase with its two all-gathers.
  *    The slod_*_device entry points remain for callers that do their own exchange.
  *  - there is NO CPU fallback: if no CUDA device is usable slod_create fails with SLOD_ERR_CUDA.
- *  - a handle is thread-compatible, not thread-safe; the kernels read their parameters from one __constant__ block
- *    per process, so compute calls of DIFFERENT handles of one process must not overlap in time either (sequential
- *    use of several handles is fine and tested).
+ *  - a handle is thread-compatible, not thread-safe (one call at a time per handle).  DIFFERENT handles may be used
+ *    concurrently from different host threads and streams, on the same device too: the kernels read their parameters
+ *    from one __constant__ block per device, and every call that launches kernels binds its handle's block for its
+ *    scope (the calls of different handles on one device enqueue one after the other; the block is re-uploaded,
+ *    stream-ordered, only when the resident bytes differ).
+ *  - patch size: any number of subdivisions and any oversampling whose patches have at most 128 coarse dofs; patches
+ *    too large for the shared-memory solvers (3-D, 4 subdivisions, oversampling 2) run through a direct banded solver
+ *    with its windows in global memory (slower), like the reference's direct solver (include/LODtools.h:575-580).
  *  - patch id == active-cell index of the centre cell after refine_global (Morton / Z-order, x low
  *    bit), exactly as in source/LOD.cc:184-192.
  *  - patch-local fine nodes are numbered lexicographically (x fastest) on the patch's own node box
