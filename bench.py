@@ -375,15 +375,27 @@ def main():
             h_phi = torch.empty((p1 - p0, s, stride), dtype=torch.float64, pin_memory=True)
             h_K = torch.empty(((p1 - p0) * s, ellw), dtype=torch.float64, pin_memory=True)
 
+            trace = os.environ.get("SLOD_E2E_TRACE") and rank == 0
+
             def e2e_step():
+                tt = [time.perf_counter()]
                 for f, tb in enumerate(tables):
                     ctx.set_coefficient(f, w["r"], tb)
+                tt.append(time.perf_counter())
                 # the library copies the rank's rows of phi / K into the pinned buffers on its own stream as soon as they
                 # are final (phi while the all-gather and the coarse kernel still run); K is all-gathered on the devices
                 ctx.set_host_outputs(h_phi.data_ptr(), 0, h_K.data_ptr())
-                step(gather_K=True)
+                ctx.offline_distributed(phi.data_ptr(), aphi.data_ptr(), K.data_ptr(), gather_phi=False, gather_K=True,
+                                        stream=stream)
+                tt.append(time.perf_counter())
+                ctx.synchronize()
+                tt.append(time.perf_counter())
                 ctx.set_host_outputs(0, 0, 0)
                 torch.cuda.synchronize()
+                tt.append(time.perf_counter())
+                if trace:
+                    print("e2e trace ms: set_coefficient %.2f  enqueue %.2f  slod_synchronize %.2f  cuda sync %.2f" %
+                          tuple(1e3 * (b_ - a_) for a_, b_ in zip(tt[:-1], tt[1:])), file=sys.stderr, flush=True)
                 return float(h_K[0, 0] + h_phi[0, 0, 0])
             d2h = (p1 - p0) * s * (ellw + stride) * 8 * world
             path = ("per rank: slod_set_coefficient + slod_offline_distributed (NCCL all-gather of A*phi inside the library) + "

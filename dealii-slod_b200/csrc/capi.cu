@@ -435,6 +435,10 @@ int prepare_coefficients(slod_ctx *ctx) {
       const int ratio = nl / ns;
       return sub * ratio + (int)std::floor(gp[qbit] * ratio);
     };
+    if (nl == ns && nq == 1) {   // one table cell per fine sub-cell: the table is the fine array
+      std::copy(tab.begin(), tab.end(), out);
+      continue;
+    }
     for (int z = 0; z < nz; ++z)
       for (int y = 0; y < ns; ++y)
         for (int x = 0; x < ns; ++x)

@@ -19,3 +19,4 @@ for rep in range(4):
     t.append(time.perf_counter())
     d = np.diff(t) * 1e3
     print("set_coef %.1f  compute_basis %.1f  assemble_coarse %.1f  all_basis %.1f  coarse_csr %.1f  total %.1f ms" % (*d, d.sum()), flush=True)
+    print("  kernel ms", [round(float(x), 2) for x in ctx.timings()[:8]], flush=True)
