@@ -813,13 +813,14 @@ k_coarse(int patch_begin, int patch_end, const double *__restrict__ phi, const d
 // each member's own box), so every A*phi value of a neighbour is loaded once per group and multiplied with all
 // members' phi at the same shared-memory offset: no per-pair index arithmetic, 2^dim times less L2 traffic.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCoarseThreads = 1024;   // 32 warps: the kernel is bound by the latency of its L2 / shared-memory loads
+constexpr int kCoarseThreads = 512;
 template <int DIM, int S>
 __global__ void __launch_bounds__(kCoarseThreads, 1)
 k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi, const double *__restrict__ aphi,
                  double *__restrict__ Kell, FinishLayout lay, int NU) {
   constexpr int NG = 1 << DIM;   // patches per group
-  constexpr int NA = NG * S;     // accumulators per lane: (member, component d)
+  constexpr int NA = NG * S;     // accumulators per lane and neighbour: (member, component d)
+  constexpr int NQ = 4;          // neighbours (adjacent in x) per warp pass (3: no spills but 8.3 instead of 7.7 ms)
   extern __shared__ double smem[];
   const int NUV = (DIM == 3) ? NU * NU * NU : NU * NU;
   double *sU = smem;  // [NA][NUV][S]
@@ -871,63 +872,103 @@ k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi,
       }
     }
     __syncthreads();
-    // neighbour cells of the group: [base - w, base + 1 + w] per axis
+    // neighbour cells of the group: [base - w, base + 1 + w] per axis.  A warp takes NQ neighbours that are adjacent
+    // in x at a time: they share the y / z extents of their sweep boxes, so one pass over the union of the boxes loads
+    // every staged phi value once for all of them (the kernel is bound by its shared-memory loads: 8 per A*phi value
+    // with one neighbour at a time, 8 per NQ values now).
     const int bx = sGeo[0][3], by = sGeo[0][4], bz = sGeo[0][5];  // member 0 = lowest corner of the 2^dim block
     const int span = 2 * w + 2;
-    const int nq = (DIM == 3) ? span * span * span : span * span;
-    for (int qi = warp; qi < nq; qi += nwarp) {
-      int qc[3] = {bx - w + qi % span, by - w + (qi / span) % span, (DIM == 3) ? bz - w + qi / (span * span) : 0};
-      bool inside = true;
+    const int ngx = (span + NQ - 1) / NQ;
+    const int ngrp = ngx * span * ((DIM == 3) ? span : 1);
+    for (int gi = warp; gi < ngrp; gi += nwarp) {
+      const int qx0 = bx - w + NQ * (gi % ngx), qy = by - w + (gi / ngx) % span, qz = (DIM == 3) ? bz - w + gi / (ngx * span) : 0;
+      if (qy < 0 || qy >= cP.N || qz < 0 || qz >= cP.N) continue;
+      // per neighbour: id, x range of the sweep box (global node coordinates), row length; y / z from the first valid one
+      int qid[NQ], x0[NQ], x1[NQ], lox[NQ], px[NQ];
+      int b0y = 0, b1y = -1, b0z = 0, b1z = -1, loy = 0, loz = 0, py = 1;
+      int ux0 = 1 << 30, ux1 = -1;
+      bool got = false;
 #pragma unroll
-      for (int a = 0; a < DIM; ++a) inside = inside && (qc[a] >= 0 && qc[a] < cP.N);
-      if (!inside) continue;
-      const int qid = (int)morton_fast(qc, DIM);
-      const Geom gq = make_geom_at(cP, qc);
-      // sweep box = box(q) /\ common box, in global node coordinates
-      int b0[3], b1[3];
-      bool any = true;
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if (a < DIM) {
-          b0[a] = max(gq.lo[a] * n, ulo[a]);
-          b1[a] = min((gq.lo[a] + gq.m[a]) * n, uhi[a]);
-          if (b1[a] < b0[a]) any = false;
-        } else {
-          b0[a] = 0; b1[a] = 0;
+      for (int j = 0; j < NQ; ++j) {
+        const int qc[3] = {qx0 + j, qy, qz};
+        x0[j] = 1; x1[j] = 0; qid[j] = 0; lox[j] = 0; px[j] = 1;
+        if (NQ * (gi % ngx) + j >= span || qc[0] < 0 || qc[0] >= cP.N) continue;
+        const Geom gq = make_geom_at(cP, qc);
+        x0[j] = max(gq.lo[0] * n, ulo[0]);
+        x1[j] = min((gq.lo[0] + gq.m[0]) * n, uhi[0]);
+        if (x1[j] < x0[j]) continue;
+        qid[j] = (int)morton_fast(qc, DIM);
+        lox[j] = gq.lo[0] * n;
+        px[j] = gq.p[0];
+        ux0 = min(ux0, x0[j]);
+        ux1 = max(ux1, x1[j]);
+        if (!got) {
+          got = true;
+          b0y = max(gq.lo[1] * n, ulo[1]);
+          b1y = min((gq.lo[1] + gq.m[1]) * n, uhi[1]);
+          loy = gq.lo[1] * n;
+          py = gq.p[1];
+          if (DIM == 3) {
+            b0z = max(gq.lo[2] * n, ulo[2]);
+            b1z = min((gq.lo[2] + gq.m[2]) * n, uhi[2]);
+            loz = gq.lo[2] * n;
+          } else {
+            b0z = 0; b1z = 0; loz = 0;
+          }
         }
       }
-      const int ex = any ? b1[0] - b0[0] + 1 : 0, ey = b1[1] - b0[1] + 1, ez = b1[2] - b0[2] + 1;
-      const int sq_ = gq.p[0] * gq.p[1] * S;
+      if (!got || b1y < b0y || b1z < b0z) continue;
+      const int exu = ux1 - ux0 + 1, ey = b1y - b0y + 1, ez = b1z - b0z + 1;
       for (int e = 0; e < S; ++e) {
-        double acc[NA];
+        double acc[NQ][NA];
 #pragma unroll
-        for (int k = 0; k < NA; ++k) acc[k] = 0.0;
-        const double *aq = aphi + ((size_t)qid * S + e) * lay.nf_max;
-        for (int t = lane; t < ex * ey; t += 32) {
-          const int iy = t / ex, ix = t - iy * ex;
-          const int gx = b0[0] + ix, gy = b0[1] + iy;
-          const double *q1 = aq + ((((b0[2] - gq.lo[2] * n)) * gq.p[1] + (gy - gq.lo[1] * n)) * gq.p[0] + (gx - gq.lo[0] * n)) * S;
-          const double *u1 = sU + (((b0[2] - ulo[2]) * NU + (gy - ulo[1])) * NU + (gx - ulo[0])) * S;
+        for (int j = 0; j < NQ; ++j)
+#pragma unroll
+          for (int k = 0; k < NA; ++k) acc[j][k] = 0.0;
+        for (int t = lane; t < exu * ey; t += 32) {
+          const int iy = t / exu, ix = t - iy * exu;
+          const int gx = ux0 + ix, gy = b0y + iy;
+          const double *u1 = sU + (((b0z - ulo[2]) * NU + (gy - ulo[1])) * NU + (gx - ulo[0])) * S;
+          const double *q1[NQ];
+          int sq[NQ];
+          bool in[NQ];
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            in[j] = gx >= x0[j] && gx <= x1[j];
+            sq[j] = px[j] * py * S;
+            q1[j] = aphi + ((size_t)qid[j] * S + e) * lay.nf_max +
+                    (((b0z - loz) * py + (gy - loy)) * px[j] + (in[j] ? gx - lox[j] : 0)) * S;
+          }
           for (int iz = 0; iz < ez; ++iz) {
 #pragma unroll
             for (int c = 0; c < S; ++c) {
-              const double v = q1[iz * sq_ + c];
+              double v[NQ];
+#pragma unroll
+              for (int j = 0; j < NQ; ++j) v[j] = in[j] ? q1[j][iz * sq[j] + c] : 0.0;
               const double *u = u1 + iz * NU * NU * S + c;
 #pragma unroll
-              for (int k = 0; k < NA; ++k) acc[k] += v * u[(size_t)k * NUV * S];
+              for (int k = 0; k < NA; ++k) {
+                const double uk = u[(size_t)k * NUV * S];
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) acc[j][k] += v[j] * uk;
+              }
             }
           }
         }
-        const double val = warp_sum_packed(acc, lane);   // lane L holds pair warp_sum_index<NA>(L)
-        if ((lane & (NA == 8 ? 3 : 7)) == 0) {
-          // pair k = (member k / S, component k % S)
-          const int k = warp_sum_index<NA>(lane);
-          const int mem = k / S, d = k - mem * S;
-          if (sGeo[mem][7]) {
-            const int Dx = qc[0] - sGeo[mem][3], Dy = qc[1] - sGeo[mem][4], Dz = (DIM == 3) ? qc[2] - sGeo[mem][5] : 0;
-            if (abs(Dx) <= w && abs(Dy) <= w && abs(Dz) <= w) {
-              const int slot = (DIM == 3) ? ((Dz + w) * ww + (Dy + w)) * ww + (Dx + w) : (Dy + w) * ww + (Dx + w);
-              Kell[((size_t)sGeo[mem][6] * S + d) * cP.ell_width + slot * S + e] = val;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          if (x1[j] < x0[j]) continue;   // warp uniform
+          const double val = warp_sum_packed(acc[j], lane);   // lane L holds pair warp_sum_index<NA>(L)
+          if ((lane & (NA == 8 ? 3 : 7)) == 0) {
+            // pair k = (member k / S, component k % S)
+            const int k = warp_sum_index<NA>(lane);
+            const int mem = k / S, d = k - mem * S;
+            if (sGeo[mem][7]) {
+              const int Dx = qx0 + j - sGeo[mem][3], Dy = qy - sGeo[mem][4], Dz = (DIM == 3) ? qz - sGeo[mem][5] : 0;
+              if (abs(Dx) <= w && abs(Dy) <= w && abs(Dz) <= w) {
+                const int slot = (DIM == 3) ? ((Dz + w) * ww + (Dy + w)) * ww + (Dx + w) : (Dy + w) * ww + (Dx + w);
+                Kell[((size_t)sGeo[mem][6] * S + d) * cP.ell_width + slot * S + e] = val;
+              }
             }
           }
         }
@@ -935,7 +976,6 @@ k_coarse_blocked(int patch_begin, int patch_end, const double *__restrict__ phi,
     }
   }
 }
-
 template <int DIM, int S>
 static cudaError_t launch_coarse_blocked_t(int grid, size_t smem, cudaStream_t st, int p0, int p1, const double *phi,
                                            const double *aphi, double *Kell, const FinishLayout &lay, int NU) {
