@@ -117,13 +117,13 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
       {
         const int rows_per_pass = NT / (NC / 2);  // 4 for 128 columns
         const int c2 = tid % (NC / 2), rbase = tid / (NC / 2);
-        for (int r0 = rbase; r0 < kFTB; r0 += 4 * rows_per_pass) {
+        for (int r0 = 4 * rbase; r0 < kFTB; r0 += 4 * rows_per_pass) {   // four CONSECUTIVE rows per thread
           double2 acc[4];
           int cmax = 0;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             acc[u] = make_double2(0.0, 0.0);
-            const int rb = r0 + u * rows_per_pass;
+            const int rb = r0 + u;
             if (rb < kFTB) cmax = max(cmax, sAcnt[rb]);
           }
           if (2 * c2 >= ncd) cmax = 0;
@@ -131,7 +131,7 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
           for (int e = 0; e < cmax; ++e) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int rb = min(r0 + u * rows_per_pass, kFTB - 1);
+              const int rb = min(r0 + u, kFTB - 1);
               const double av = sArow[rb * kFNB + e];
               const double2 xv = *reinterpret_cast<const double2 *>(X + (size_t)sAnbr[rb * kFNB + e] * lay.ldx + 2 * c2);
               acc[u].x += av * xv.x;
@@ -142,7 +142,7 @@ k_patch_flux(const int *__restrict__ patch_ids, int n_work, const double *__rest
           // padding columns carry zeros (empty stencil lists / cmax = 0)
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int rb = r0 + u * rows_per_pass;
+            const int rb = r0 + u;
             if (rb < kFTB && t0 + rb < nbd_pad)   // W holds round_up(nbd, 32) rows: dense_mma streams tiles of 32
               *reinterpret_cast<double2 *>(W + (size_t)(t0 + rb) * lay.ldx + 2 * c2) = acc[u];
           }
