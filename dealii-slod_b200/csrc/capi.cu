@@ -963,6 +963,13 @@ int slod_create(const slod_params *par, slod_ctx **out) {
         delete ctx;
         return bad(SLOD_ERR_UNSUPPORTED, "a patch has no interior fine dof (n_subdivisions = 1 with one-cell patches)");
       }
+      if (g.Ni < g.Ncd) {
+        // M = P_i^T A_ii^{-1} P_i / H^d has rank <= Ni: with fewer interior fine dofs than coarse dofs it is singular and
+        // the reference's gauss_jordan (source/LOD.cc:553) has nothing to invert either (n_subdivisions = 1)
+        delete ctx;
+        return bad(SLOD_ERR_UNSUPPORTED,
+                   "a patch has fewer interior fine dofs than coarse dofs: P^T A^-1 P is singular (use n_subdivisions >= 2)");
+      }
       bw_max = std::max(bw_max, g.bw);
       int nb = 0;
       // patch-boundary dofs
@@ -1007,6 +1014,11 @@ int slod_create(const slod_params *par, slod_ctx **out) {
     else if (rb_need <= 4 && nw_need <= 4) { variant = 1; rbmax = 4; nw = 4; }
     else if (rb_need <= 4 && nw_need <= 8) { variant = 2; rbmax = 4; nw = 8; }
     if (getenv("SLOD_FORCE_SIMT_SOLVER") || getenv("SLOD_FORCE_GMEM_SOLVER")) variant = -1;
+    // a variant whose shared-memory plan does not fit (large coefficient windows: many subdivisions) is no variant: the
+    // SIMT solver takes over, with its windows in global memory if need be
+    if (variant >= 0 && solve_mma_smem(variant, coef_doubles, ((P.NiMax + 7) / 8) * 8, P.s * ((P.dim == 3) ? 13 : 4) + P.s) >
+                            prop.sharedMemPerBlockOptin)
+      variant = -1;
     if (variant >= 0) {
       ctx->mma_variant = variant;
       ctx->mma_threads = 32 * nw;

@@ -54,6 +54,13 @@ def test_parameter_validation(lib):
         with pytest.raises(pkg.SlodError) as e:
             pkg.SlodContext(device=-2, **kw)
         assert e.value.code == 2 and "interior" in str(e.value)
+    # fewer interior fine dofs than coarse dofs on some patch: P^T A^-1 P is singular (the reference's gauss_jordan,
+    # source/LOD.cc:553, cannot invert it either) -- refused with a clear message instead of a numerical failure later
+    for kw in (dict(dim=2, n_global_refinements=3, n_subdivisions=1, oversampling=1),
+               dict(dim=3, n_global_refinements=2, n_subdivisions=1, oversampling=1)):
+        with pytest.raises(pkg.SlodError) as e:
+            pkg.SlodContext(device=-2, **kw)
+        assert e.value.code == 2 and "singular" in str(e.value)
 
 
 @pytest.mark.parametrize("dim,s,ref,n,ell", [(2, 1, 3, 2, 1), (2, 1, 4, 2, 2), (2, 2, 3, 2, 1), (2, 1, 2, 4, 1),

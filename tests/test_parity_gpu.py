@@ -73,6 +73,8 @@ CASES = [
     dict(dim=3, s=1, ref=2, n=2, ell=1),
     dict(dim=3, s=1, ref=3, n=2, ell=2, sample=10, kind="uniform1e4", seed=3001),   # cfg 4 shape
     dict(dim=3, s=1, ref=2, n=2, ell=2, sample=16),                  # 4^3 cells: patches of 27 .. 64 cells (tensor-core solver + SIMT dense stage)
+    dict(dim=2, s=1, ref=4, n=8, ell=2, sample=8),                   # 8 subdivisions: the tensor-core plan does not fit -> SIMT solver
+    dict(dim=2, s=2, ref=3, n=8, ell=1, sample=8),                   # elasticity, 8 subdivisions
     # patches too large for the shared-memory solvers (Ni = 3375, half band width 241): windows in global memory
     dict(dim=3, s=1, ref=2, n=4, ell=2, sample=6),
     # the same fall-back forced on small shapes (SIMT solver with global windows, SIMT dense with a global coefficient window)
