@@ -31,7 +31,8 @@
  *    from one __constant__ block per device, and every call that launches kernels binds its handle's block for its
  *    scope (the calls of different handles on one device enqueue one after the other; the block is re-uploaded,
  *    stream-ordered, only when the resident bytes differ).
- *  - patch size: any number of subdivisions and any oversampling whose patches have at most 128 coarse dofs; patches
+ *  - patch size: n_subdivisions >= 2 (with 1 the matrix P^T A^-1 P of some patch is singular: refused with
+ *    SLOD_ERR_UNSUPPORTED) and any oversampling whose patches have at most 128 coarse dofs; patches
  *    too large for the shared-memory solvers (3-D, 4 subdivisions, oversampling 2) run through a direct banded solver
  *    with its windows in global memory (slower), like the reference's direct solver (include/LODtools.h:575-580).
  *  - patch id == active-cell index of the centre cell after refine_global (Morton / Z-order, x low
